@@ -1,0 +1,631 @@
+// api.cu - the C ABI (include/easydgl_b200.h): handle, weight binding, workspace, and the kernel
+// pipelines for EasyDGL.__call__ (EasyDGL.py:69-151), CTSMA.__call__ (CTSMA.py:46-91) and the ranking
+// part of Sequential.eval (Base.py:150-181).
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/easydgl_b200.h"
+#include "common.cuh"
+
+namespace edgl {
+
+std::atomic<long long> g_launches{0};
+
+std::string& last_error() {
+  static thread_local std::string e;
+  return e;
+}
+
+int set_error(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  last_error() = buf;
+  return code;
+}
+
+struct Tensor {
+  const void* p = nullptr;
+  long long numel = 0;
+};
+
+}  // namespace edgl
+
+using namespace edgl;
+
+struct edgl_handle {
+  edgl_config cfg;
+  int dev = 0;
+  int L = 0, d = 0, h = 0, dh = 0, E = 0, N1 = 0, K = 0, ts_len = 0;
+  int Ka = 0;            // width of the fused block-0 input: d + E (EasyDGL) or 2d (CTSMA)
+  long long c0 = 0, c1 = 0;  // logit columns owned by this handle
+  std::map<std::string, Tensor> mt;                // model-level tensors
+  std::vector<std::map<std::string, Tensor>> bt;   // per-block tensors
+  bool committed = false;
+  // derived (owned)
+  float* tscale = nullptr;
+  uint8_t* mark8 = nullptr;
+  int* flag = nullptr;
+  float* bias_full = nullptr;  // [N1] = concat([-1000], output_bias)  (Base.py:110)
+  float* wfold0 = nullptr;     // EasyDGL block 0: [Ka,4d]
+  float* pbias0 = nullptr;     // EasyDGL block 0: [L,4d] = pos_embs @ W[d:2d] + b
+  std::vector<float*> wkvt, bkvt;  // CTSMA: packed [Cin,3d], [3d]
+  // workspace (owned)
+  float *xa = nullptr, *p0 = nullptr, *p1 = nullptr, *p2 = nullptr, *qkvt = nullptr, *spans = nullptr, *y = nullptr,
+        *logits_ws = nullptr;
+  uint8_t *marks = nullptr, *kmask = nullptr;
+  long long ws_rows = 0;  // rows of logits_ws
+  // staging for the *_host entry point
+  int64_t* st_ids = nullptr;
+  float* st_ts = nullptr;
+  int32_t* st_idx = nullptr;
+  float* st_val = nullptr;
+  std::vector<void*> owned;
+};
+
+namespace {
+
+template <typename T>
+int dev_alloc(edgl_handle* h, T** p, size_t n) {
+  void* q = nullptr;
+  if (n == 0) n = 1;
+  cudaError_t e = cudaMalloc(&q, n * sizeof(T));
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return set_error(EDGL_ENOMEM, "cudaMalloc of %zu bytes failed: %s", n * sizeof(T), cudaGetErrorString(e));
+  }
+  h->owned.push_back(q);
+  *p = reinterpret_cast<T*>(q);
+  return 0;
+}
+
+int cin_of(const edgl_handle* h, int block) {
+  if (h->cfg.model == EDGL_MODEL_EASYDGL) return block == 0 ? 3 * h->d : h->d;
+  return block == 0 ? 2 * h->d : h->d;
+}
+
+// expected element count of a named tensor; -1 = unknown name
+long long expected_numel(const edgl_handle* h, const std::string& n, int block) {
+  const long long d = h->d, E = h->E, dh = h->dh, L = h->L, N1 = h->N1;
+  const bool easy = h->cfg.model == EDGL_MODEL_EASYDGL;
+  if (block < 0) {
+    if (n == "item_embs") return N1 * d;
+    if (n == "pos_embs") return L * d;
+    if (n == "output_bias") return N1 - 1;
+    if (n == "mark_table") return (long long)h->cfg.mark_rows * E;
+    if (easy) {
+      if (n == "mark_embs") return E * d;
+      if (n == "tr_w") return d * d;
+      if (n == "tr_b" || n == "tr_ln_g" || n == "tr_ln_b") return d;
+    } else {
+      if (n == "out_ln_g" || n == "out_ln_b") return d;
+    }
+    return -1;
+  }
+  const long long cin = cin_of(h, block);
+  if (n == "int_w") return (dh + 1) * dh * E;
+  if (n == "int_b") return dh * E;
+  if (n == "int_weight") return E * dh;
+  if (n == "int_scaling") return E;
+  if (easy) {
+    if (n == "qkvt_w") return cin * 4 * d;
+    if (n == "qkvt_b") return 4 * d;
+    if (n == "ao_w") return d * d;
+    if (n == "ao_b" || n == "ao_ln_g" || n == "ao_ln_b" || n == "ff2_b" || n == "ff_ln_g" || n == "ff_ln_b") return d;
+    if (n == "ff1_w" || n == "ff2_w") return 2 * d * d;
+    if (n == "ff1_b") return 2 * d;
+  } else {
+    if (n == "ln1_g" || n == "ln1_b") return cin;
+    if (n == "q_w" || n == "k_w" || n == "v_w" || n == "t_w") return cin * d;
+    if (n == "q_b" || n == "k_b" || n == "v_b" || n == "t_b" || n == "ln2_g" || n == "ln2_b" || n == "ff1_b" ||
+        n == "ff2_b")
+      return d;
+    if (n == "ff1_w" || n == "ff2_w") return d * d;
+  }
+  return -1;
+}
+
+const char* const kModelNamesEasy[] = {"item_embs", "pos_embs", "output_bias", "mark_table", "mark_embs",
+                                       "tr_w", "tr_b", "tr_ln_g", "tr_ln_b"};
+const char* const kModelNamesCtsma[] = {"item_embs", "pos_embs", "output_bias", "mark_table", "out_ln_g", "out_ln_b"};
+const char* const kBlockNamesEasy[] = {"int_w", "int_b", "int_weight", "int_scaling", "qkvt_w", "qkvt_b", "ao_w",
+                                       "ao_b", "ao_ln_g", "ao_ln_b", "ff1_w", "ff1_b", "ff2_w", "ff2_b",
+                                       "ff_ln_g", "ff_ln_b"};
+const char* const kBlockNamesCtsma[] = {"int_w", "int_b", "int_weight", "int_scaling", "ln1_g", "ln1_b", "q_w",
+                                        "q_b", "k_w", "k_b", "v_w", "v_b", "t_w", "t_b", "ln2_g", "ln2_b",
+                                        "ff1_w", "ff1_b", "ff2_w", "ff2_b"};
+
+inline const float* F(const std::map<std::string, Tensor>& m, const char* n) {
+  return reinterpret_cast<const float*>(m.at(n).p);
+}
+
+int check_ready(const edgl_handle* h, int B, bool need_batch_fit = true) {
+  if (!h) return set_error(EDGL_EINVAL, "null handle");
+  if (!h->committed) return set_error(EDGL_ESTATE, "edgl_commit has not been called after the last edgl_set_tensor");
+  if (B < 0 || (need_batch_fit && B > h->cfg.max_batch))
+    return set_error(EDGL_EINVAL, "batch %d outside [0, max_batch=%d]", B, h->cfg.max_batch);
+  return 0;
+}
+
+int dense(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc, long long M, int N,
+          int K, int act, const float* R, int ldr, cudaStream_t st) {
+  GemmArgs g;
+  g.A = A; g.lda = lda; g.W = W; g.ldw = ldw; g.C = C; g.ldc = ldc;
+  g.M = (int)M; g.N = N; g.K = K; g.bias = bias; g.act = act; g.R = R; g.ldr = ldr;
+  return launch_gemm(g, st);
+}
+
+AttnArgs attn_args(const edgl_handle* h, const std::map<std::string, Tensor>& w, const float* qkvt, const uint8_t* kmask,
+                   const float* spans, const uint8_t* marks, const float* R, int ldr, float* O, float* lam, int B,
+                   bool causal, bool diag_one) {
+  AttnArgs a;
+  const int d = h->d;
+  a.Q = qkvt; a.K = qkvt + d; a.V = qkvt + 2 * d; a.T = qkvt + 3 * d;
+  a.ldq = a.ldk = a.ldv = a.ldt = 4 * d;
+  a.kmask = kmask; a.spans = spans; a.marks = marks; a.R = R; a.ldr = ldr;
+  a.int_w = F(w, "int_w"); a.int_b = F(w, "int_b"); a.int_weight = F(w, "int_weight");
+  a.int_scaling = F(w, "int_scaling");
+  a.O = O; a.ldo = d; a.lam = lam; a.B = B; a.L = h->L; a.d = d; a.h = h->h; a.E = h->E;
+  a.causal = causal; a.diag_one = diag_one;
+  return a;
+}
+
+EmbedArgs embed_args(const edgl_handle* h, const int64_t* ids, const float* ts, int B) {
+  EmbedArgs e;
+  memset(&e, 0, sizeof(e));
+  e.model = h->cfg.model; e.ids = ids; e.ts = ts; e.B = B; e.L = h->L; e.ts_len = h->ts_len; e.d = h->d; e.E = h->E;
+  e.time_scale = h->cfg.time_scale; e.mask_id = h->cfg.mask_id;
+  e.item_table = F(h->mt, "item_embs"); e.num_rows = h->N1; e.pos_table = F(h->mt, "pos_embs");
+  e.mark_embs = h->cfg.model == EDGL_MODEL_EASYDGL ? F(h->mt, "mark_embs") : nullptr;
+  e.mark_table8 = h->mark8; e.mark_rows = h->cfg.mark_rows; e.tscale = h->tscale;
+  return e;
+}
+
+// EasyDGL.__call__ up to y = hidden[:, -1]  (EasyDGL.py:69-146)
+int encode_easydgl(edgl_handle* h, const int64_t* ids, const float* ts, int B, float* y, cudaStream_t st) {
+  const int d = h->d, L = h->L;
+  const long long rows = (long long)B * L;
+  EmbedArgs e = embed_args(h, ids, ts, B);
+  e.Xa = h->xa; e.ldxa = h->Ka; e.spans = h->spans; e.marks = h->marks; e.kmask = h->kmask;
+  EDGL_TRY(launch_embed(e, st));
+  const float* cur = h->xa;
+  int ldcur = h->Ka;
+  for (int i = 0; i < h->cfg.num_blocks; ++i) {
+    const auto& w = h->bt[i];
+    if (i == 0) {
+      // QKVT = X0 @ W + b with the position / mark-code thirds of X0 folded (commit()): temporal.py:409
+      GemmArgs g;
+      g.A = h->xa; g.lda = h->Ka; g.W = h->wfold0; g.ldw = 4 * d; g.C = h->qkvt; g.ldc = 4 * d;
+      g.M = (int)rows; g.N = 4 * d; g.K = h->Ka; g.pbias = h->pbias0; g.pperiod = L;
+      EDGL_TRY(launch_gemm(g, st));
+    } else {
+      EDGL_TRY(dense(cur, ldcur, F(w, "qkvt_w"), 4 * d, F(w, "qkvt_b"), h->qkvt, 4 * d, rows, 4 * d, d, ACT_NONE,
+                     nullptr, 0, st));
+    }
+    AttnArgs a = attn_args(h, w, h->qkvt, h->kmask, h->spans, h->marks, cur, ldcur, h->p0, nullptr, B, false, true);
+    EDGL_TRY(launch_attention(a, st));                                                   // temporal.py:412-447
+    EDGL_TRY(dense(h->p0, d, F(w, "ao_w"), d, F(w, "ao_b"), h->p1, d, rows, d, d, ACT_NONE, cur, ldcur, st));  // :113,116
+    EDGL_TRY(launch_layernorm(h->p1, F(w, "ao_ln_g"), F(w, "ao_ln_b"), B, L, d, h->p0, false, st));            // :116
+    EDGL_TRY(dense(h->p0, d, F(w, "ff1_w"), 2 * d, F(w, "ff1_b"), h->p2, 2 * d, rows, 2 * d, d, ACT_GELU, nullptr, 0,
+                   st));                                                                 // :120-121
+    EDGL_TRY(dense(h->p2, 2 * d, F(w, "ff2_w"), d, F(w, "ff2_b"), h->p1, d, rows, d, 2 * d, ACT_NONE, h->p0, d, st));  // :125,128
+    EDGL_TRY(launch_layernorm(h->p1, F(w, "ff_ln_g"), F(w, "ff_ln_b"), B, L, d, h->p2, false, st));            // :128
+    cur = h->p2;
+    ldcur = d;
+  }
+  EDGL_TRY(dense(cur, ldcur, F(h->mt, "tr_w"), d, F(h->mt, "tr_b"), h->p0, d, rows, d, d, ACT_GELU, nullptr, 0, st));  // :138
+  EDGL_TRY(launch_layernorm(h->p0, F(h->mt, "tr_ln_g"), F(h->mt, "tr_ln_b"), B, L, d, y, true, st));  // :139,146
+  return 0;
+}
+
+// CTSMA.__call__ up to y (CTSMA.py:46-87)
+int encode_ctsma(edgl_handle* h, const int64_t* ids, const float* ts, int B, float* y, cudaStream_t st) {
+  const int d = h->d, L = h->L;
+  const long long rows = (long long)B * L;
+  EmbedArgs e = embed_args(h, ids, ts, B);
+  e.X0 = h->p2; e.ldx0 = 2 * d; e.spans = h->spans; e.marks = h->marks; e.kmask = h->kmask;
+  EDGL_TRY(launch_embed(e, st));
+  float* cur = h->p2;
+  int cin = 2 * d;
+  for (int i = 0; i < h->cfg.num_blocks; ++i) {
+    const auto& w = h->bt[i];
+    EDGL_TRY(launch_layernorm(cur, F(w, "ln1_g"), F(w, "ln1_b"), B, L, cin, h->p0, false, st));  // CTSMA.py:68
+    EDGL_TRY(dense(h->p0, cin, F(w, "q_w"), d, F(w, "q_b"), h->qkvt, 4 * d, rows, d, cin, ACT_NONE, nullptr, 0, st));
+    EDGL_TRY(dense(cur, cin, h->wkvt[i], 3 * d, h->bkvt[i], h->qkvt + d, 4 * d, rows, 3 * d, cin, ACT_NONE, nullptr,
+                   0, st));                                                              // temporal.py:340-343
+    AttnArgs a = attn_args(h, w, h->qkvt, h->kmask, h->spans, h->marks, h->p0, cin, h->p1, nullptr, B, true, false);
+    EDGL_TRY(launch_attention(a, st));                                                   // temporal.py:345-385
+    EDGL_TRY(launch_layernorm(h->p1, F(w, "ln2_g"), F(w, "ln2_b"), B, L, d, h->p0, false, st));  // CTSMA.py:73
+    EDGL_TRY(dense(h->p0, d, F(w, "ff1_w"), d, F(w, "ff1_b"), h->p1, d, rows, d, d, ACT_RELU, nullptr, 0, st));  // Base.py:79
+    EDGL_TRY(dense(h->p1, d, F(w, "ff2_w"), d, F(w, "ff2_b"), h->p2, d, rows, d, d, ACT_NONE, h->p0, d, st));    // Base.py:83,86
+    cur = h->p2;
+    cin = d;
+  }
+  EDGL_TRY(launch_layernorm(cur, F(h->mt, "out_ln_g"), F(h->mt, "out_ln_b"), B, L, d, y, true, st));  // CTSMA.py:80,87
+  return 0;
+}
+
+int encode(edgl_handle* h, const int64_t* ids, const float* ts, int B, float* y, cudaStream_t st) {
+  if (B == 0) return 0;
+  return h->cfg.model == EDGL_MODEL_EASYDGL ? encode_easydgl(h, ids, ts, B, y, st) : encode_ctsma(h, ids, ts, B, y, st);
+}
+
+// logits[r0:r0+rc, c0:c1] = y @ table[c0:c1]^T + bias   (EasyDGL.py:149-150 / CTSMA.py:89-90, Base.py:106-110)
+int logits_rows(edgl_handle* h, const float* y, long long rc, float* out, int ldo, cudaStream_t st) {
+  GemmArgs g;
+  g.A = y; g.lda = h->d;
+  g.W = F(h->mt, "item_embs") + h->c0 * h->d; g.ldw = h->d; g.w_is_nk = true;
+  g.zero_wrow0 = (h->c0 == 0);  // zero_pad=True: row 0 of the tied table is zeros (coding.py:56-57)
+  g.C = out; g.ldc = ldo; g.M = (int)rc; g.N = (int)(h->c1 - h->c0); g.K = h->d;
+  g.bias = h->bias_full + h->c0;
+  return launch_gemm(g, st);
+}
+
+int logits_topk(edgl_handle* h, const float* y, const int64_t* seen, int seen_len, long long Bt, int32_t* idx,
+                float* val, cudaStream_t st) {
+  const int Ns = (int)(h->c1 - h->c0);
+  for (long long r0 = 0; r0 < Bt; r0 += h->ws_rows) {
+    const long long rc = (Bt - r0 < h->ws_rows) ? (Bt - r0) : h->ws_rows;
+    EDGL_TRY(logits_rows(h, y + r0 * h->d, rc, h->logits_ws, Ns, st));
+    if (seen)
+      EDGL_TRY(launch_mask_seen(h->logits_ws, Ns, (int)rc, seen + r0 * seen_len, seen_len, h->c0, h->c1, st));
+    EDGL_TRY(launch_topk(h->logits_ws, Ns, (int)rc, Ns, h->K, (int)h->c0, idx + r0 * h->K, val + r0 * h->K, st));
+  }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* edgl_last_error(void) { return last_error().c_str(); }
+int edgl_version(void) { return 100; }
+int64_t edgl_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int edgl_create(const edgl_config* cfg, edgl_handle** out) {
+  if (!cfg || !out) return set_error(EDGL_EINVAL, "null argument");
+  *out = nullptr;
+  EDGL_REQUIRE(cfg->model == EDGL_MODEL_EASYDGL || cfg->model == EDGL_MODEL_CTSMA,
+               "The ranking model: %d not implemented", cfg->model);  // util.py:96
+  EDGL_REQUIRE(cfg->max_batch >= 1 && cfg->seq_len >= 1 && cfg->num_units >= 4 && cfg->num_heads >= 1 &&
+                   cfg->num_blocks >= 1 && cfg->num_events >= 1 && cfg->num_rows >= 2 && cfg->mark_rows >= 1 &&
+                   cfg->topk >= 1,
+               "edgl_create: non-positive size in config");
+  EDGL_REQUIRE(cfg->num_units % cfg->num_heads == 0, "num_units %d not divisible by num_heads %d", cfg->num_units,
+               cfg->num_heads);
+  EDGL_REQUIRE(cfg->num_units % 4 == 0, "num_units must be a multiple of 4 (got %d)", cfg->num_units);
+  EDGL_REQUIRE(cfg->shard_world >= 1 && cfg->shard_rank >= 0 && cfg->shard_rank < cfg->shard_world,
+               "bad shard rank/world %d/%d", cfg->shard_rank, cfg->shard_world);
+  EDGL_REQUIRE(cfg->time_scale > 0.f, "time_scale must be positive");
+  int dev = 0;
+  EDGL_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  EDGL_CUDA(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10)
+    return set_error(EDGL_EARCH, "device %d is sm_%d%d; this library is built for sm_100a only", dev, prop.major,
+                     prop.minor);
+  edgl_handle* h = new edgl_handle();
+  h->cfg = *cfg;
+  h->dev = dev;
+  h->L = cfg->seq_len; h->d = cfg->num_units; h->h = cfg->num_heads; h->dh = h->d / h->h; h->E = cfg->num_events;
+  h->N1 = cfg->num_rows; h->K = cfg->topk;
+  const bool easy = cfg->model == EDGL_MODEL_EASYDGL;
+  h->ts_len = easy ? h->L : h->L + 1;
+  h->Ka = easy ? h->d + h->E : 2 * h->d;
+  const long long per = (h->N1 + cfg->shard_world - 1) / cfg->shard_world;
+  h->c0 = per * cfg->shard_rank;
+  h->c1 = h->c0 + per < h->N1 ? h->c0 + per : h->N1;
+  if (h->c0 > h->c1) h->c0 = h->c1;
+  h->bt.resize(cfg->num_blocks);
+  h->wkvt.assign(cfg->num_blocks, nullptr);
+  h->bkvt.assign(cfg->num_blocks, nullptr);
+  const long long rows = (long long)cfg->max_batch * h->L;
+  const int d = h->d;
+  int rc = 0;
+#define EDGL_ALLOC(p, n)                         \
+  if (!rc) rc = dev_alloc(h, &(p), (size_t)(n));
+  EDGL_ALLOC(h->tscale, d / 2);
+  EDGL_ALLOC(h->mark8, (long long)cfg->mark_rows * h->E);
+  EDGL_ALLOC(h->flag, 1);
+  EDGL_ALLOC(h->bias_full, h->N1);
+  if (easy) {
+    EDGL_ALLOC(h->wfold0, (long long)h->Ka * 4 * d);
+    EDGL_ALLOC(h->pbias0, (long long)h->L * 4 * d);
+    EDGL_ALLOC(h->xa, rows * h->Ka);
+  } else {
+    for (int i = 0; i < cfg->num_blocks; ++i) {
+      EDGL_ALLOC(h->wkvt[i], (long long)cin_of(h, i) * 3 * d);
+      EDGL_ALLOC(h->bkvt[i], 3 * d);
+    }
+  }
+  EDGL_ALLOC(h->p0, rows * 2 * d);
+  EDGL_ALLOC(h->p1, rows * 2 * d);
+  EDGL_ALLOC(h->p2, rows * 2 * d);
+  EDGL_ALLOC(h->qkvt, rows * 4 * d);
+  EDGL_ALLOC(h->spans, rows);
+  EDGL_ALLOC(h->marks, rows * h->E);
+  EDGL_ALLOC(h->kmask, rows);
+  EDGL_ALLOC(h->y, (long long)cfg->max_batch * d);
+  {
+    const long long Ns = h->c1 - h->c0 > 0 ? h->c1 - h->c0 : 1;
+    const long long max_bt = (long long)cfg->max_batch * cfg->shard_world;
+    long long r = (2ll << 30) / (Ns * 4);
+    if (r < 1) r = 1;
+    if (r > max_bt) r = max_bt;
+    h->ws_rows = r;
+    EDGL_ALLOC(h->logits_ws, r * Ns);
+  }
+  EDGL_ALLOC(h->st_ids, rows);
+  EDGL_ALLOC(h->st_ts, (long long)cfg->max_batch * h->ts_len);
+  EDGL_ALLOC(h->st_idx, (long long)cfg->max_batch * h->K);
+  EDGL_ALLOC(h->st_val, (long long)cfg->max_batch * h->K);
+#undef EDGL_ALLOC
+  if (rc) {
+    edgl_destroy(h);
+    return rc;
+  }
+  *out = h;
+  return 0;
+}
+
+int edgl_destroy(edgl_handle* h) {
+  if (!h) return 0;
+  for (void* p : h->owned) cudaFree(p);
+  delete h;
+  return 0;
+}
+
+int edgl_get_config(const edgl_handle* h, edgl_config* out) {
+  if (!h || !out) return set_error(EDGL_EINVAL, "null argument");
+  *out = h->cfg;
+  return 0;
+}
+
+int edgl_set_tensor(edgl_handle* h, const char* name, int block, const void* dev_ptr, int64_t numel) {
+  if (!h || !name || !dev_ptr) return set_error(EDGL_EINVAL, "null argument");
+  EDGL_REQUIRE(block >= -1 && block < h->cfg.num_blocks, "block %d out of range", block);
+  const long long want = expected_numel(h, name, block);
+  EDGL_REQUIRE(want >= 0, "unknown tensor name '%s' (block %d)", name, block);
+  EDGL_REQUIRE(want == numel, "tensor '%s' (block %d): expected %lld elements, got %lld", name, block, want,
+               (long long)numel);
+  EDGL_REQUIRE((reinterpret_cast<uintptr_t>(dev_ptr) & 15) == 0, "tensor '%s' must be 16-byte aligned", name);
+  Tensor t;
+  t.p = dev_ptr;
+  t.numel = numel;
+  if (block < 0) h->mt[name] = t; else h->bt[block][name] = t;
+  h->committed = false;
+  return 0;
+}
+
+int edgl_commit(edgl_handle* h, void* stream) {
+  if (!h) return set_error(EDGL_EINVAL, "null handle");
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool easy = h->cfg.model == EDGL_MODEL_EASYDGL;
+  const int d = h->d, E = h->E, L = h->L;
+  // every variable of the reference graph must be bound
+  if (easy) {
+    for (const char* n : kModelNamesEasy)
+      if (!h->mt.count(n)) return set_error(EDGL_ESTATE, "tensor '%s' not set", n);
+    for (int i = 0; i < h->cfg.num_blocks; ++i)
+      for (const char* n : kBlockNamesEasy)
+        if (!h->bt[i].count(n)) return set_error(EDGL_ESTATE, "tensor '%s' of block %d not set", n, i);
+  } else {
+    for (const char* n : kModelNamesCtsma)
+      if (!h->mt.count(n)) return set_error(EDGL_ESTATE, "tensor '%s' not set", n);
+    for (int i = 0; i < h->cfg.num_blocks; ++i)
+      for (const char* n : kBlockNamesCtsma)
+        if (!h->bt[i].count(n)) return set_error(EDGL_ESTATE, "tensor '%s' of block %d not set", n, i);
+  }
+  // TimeSinusoidCoding.__init__ (coding.py:134-135): float64 power, stored as fp32
+  {
+    std::vector<float> sc(d / 2);
+    for (int j = 0; j < d / 2; ++j) sc[j] = (float)pow(10000.0, (double)(2 * j) * 1.0 / (double)d);
+    EDGL_CUDA(cudaMemcpyAsync(h->tscale, sc.data(), sc.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+    EDGL_CUDA(cudaStreamSynchronize(st));  // sc goes out of scope
+  }
+  // mark_lookup_table (EasyDGL.py:45): int64 -> uint8, values must index mark_embs (EasyDGL.py:87)
+  EDGL_CUDA(cudaMemsetAsync(h->flag, 0, sizeof(int), st));
+  EDGL_TRY(launch_mark_table_to_u8(reinterpret_cast<const int64_t*>(h->mt.at("mark_table").p),
+                                   (long long)h->cfg.mark_rows * E, h->mark8, h->flag, E, st));
+  // output_bias(inf_pad=True) (Base.py:106-110)
+  {
+    const float m1000 = -1000.f;
+    EDGL_CUDA(cudaMemcpyAsync(h->bias_full, &m1000, sizeof(float), cudaMemcpyHostToDevice, st));
+    EDGL_CUDA(cudaMemcpyAsync(h->bias_full + 1, F(h->mt, "output_bias"), (size_t)(h->N1 - 1) * sizeof(float),
+                              cudaMemcpyDeviceToDevice, st));
+  }
+  if (easy) {
+    // Block-0 input is X0 = [x | pos | mcode] (EasyDGL.py:89); pos depends only on l and mcode is
+    // linear in the mark-value histogram, so  X0 @ W = x @ W[0:d] + (pos @ W[d:2d])[l] + cnt @ (mark_embs_zp @ W[2d:3d]).
+    const auto& w = h->bt[0];
+    const float* W = F(w, "qkvt_w");
+    EDGL_CUDA(cudaMemcpyAsync(h->wfold0, W, (size_t)d * 4 * d * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    EDGL_TRY(dense(F(h->mt, "mark_embs"), d, W + (size_t)2 * d * 4 * d, 4 * d, nullptr, h->wfold0 + (size_t)d * 4 * d,
+                   4 * d, E, 4 * d, d, ACT_NONE, nullptr, 0, st));
+    EDGL_CUDA(cudaMemsetAsync(h->wfold0 + (size_t)d * 4 * d, 0, (size_t)4 * d * sizeof(float), st));  // zero_pad row 0
+    EDGL_TRY(dense(F(h->mt, "pos_embs"), d, W + (size_t)d * 4 * d, 4 * d, F(w, "qkvt_b"), h->pbias0, 4 * d, L, 4 * d, d,
+                   ACT_NONE, nullptr, 0, st));
+  } else {
+    for (int i = 0; i < h->cfg.num_blocks; ++i) {
+      const auto& w = h->bt[i];
+      const int cin = cin_of(h, i);
+      const char* wn[3] = {"k_w", "v_w", "t_w"};
+      const char* bn[3] = {"k_b", "v_b", "t_b"};
+      for (int j = 0; j < 3; ++j) {
+        EDGL_CUDA(cudaMemcpy2DAsync(h->wkvt[i] + j * d, (size_t)3 * d * sizeof(float), F(w, wn[j]),
+                                    (size_t)d * sizeof(float), (size_t)d * sizeof(float), cin,
+                                    cudaMemcpyDeviceToDevice, st));
+        EDGL_CUDA(cudaMemcpyAsync(h->bkvt[i] + j * d, F(w, bn[j]), (size_t)d * sizeof(float),
+                                  cudaMemcpyDeviceToDevice, st));
+      }
+    }
+  }
+  int flag = 0;
+  EDGL_CUDA(cudaMemcpyAsync(&flag, h->flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+  EDGL_CUDA(cudaStreamSynchronize(st));
+  if (flag) return set_error(EDGL_EINVAL, "mark_table holds values outside [0, num_events=%d)", E);
+  h->committed = true;
+  return 0;
+}
+
+int edgl_encode(edgl_handle* h, const int64_t* seqs_i, const float* seqs_t, int B, float* y, void* stream) {
+  EDGL_TRY(check_ready(h, B));
+  if (!seqs_i || !seqs_t || !y) return set_error(EDGL_EINVAL, "null argument");
+  return encode(h, seqs_i, seqs_t, B, y, (cudaStream_t)stream);
+}
+
+int edgl_forward_logits(edgl_handle* h, const int64_t* seqs_i, const float* seqs_t, int B, float* logits,
+                        void* stream) {
+  EDGL_TRY(check_ready(h, B));
+  if (!seqs_i || !seqs_t || !logits) return set_error(EDGL_EINVAL, "null argument");
+  if (B == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  EDGL_TRY(encode(h, seqs_i, seqs_t, B, h->y, st));
+  return logits_rows(h, h->y, B, logits, (int)(h->c1 - h->c0), st);
+}
+
+int edgl_forward_topk(edgl_handle* h, const int64_t* seqs_i, const float* seqs_t, int B, int mask_seen,
+                      int32_t* idx, float* val, void* stream) {
+  EDGL_TRY(check_ready(h, B));
+  if (!seqs_i || !seqs_t || !idx || !val) return set_error(EDGL_EINVAL, "null argument");
+  EDGL_REQUIRE(h->cfg.shard_world == 1, "edgl_forward_topk needs an unsharded handle; use edgl_encode + "
+               "edgl_logits_topk + edgl_topk_merge");
+  if (B == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  EDGL_TRY(encode(h, seqs_i, seqs_t, B, h->y, st));
+  return logits_topk(h, h->y, mask_seen ? seqs_i : nullptr, h->L, B, idx, val, st);
+}
+
+int edgl_forward_topk_host(edgl_handle* h, const int64_t* seqs_i_host, const float* seqs_t_host, int B,
+                           int mask_seen, int32_t* idx_host, float* val_host, void* stream) {
+  EDGL_TRY(check_ready(h, B));
+  if (!seqs_i_host || !seqs_t_host || !idx_host || !val_host) return set_error(EDGL_EINVAL, "null argument");
+  if (B == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  EDGL_CUDA(cudaMemcpyAsync(h->st_ids, seqs_i_host, (size_t)B * h->L * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+  EDGL_CUDA(cudaMemcpyAsync(h->st_ts, seqs_t_host, (size_t)B * h->ts_len * sizeof(float), cudaMemcpyHostToDevice, st));
+  EDGL_TRY(edgl_forward_topk(h, h->st_ids, h->st_ts, B, mask_seen, h->st_idx, h->st_val, stream));
+  EDGL_CUDA(cudaMemcpyAsync(idx_host, h->st_idx, (size_t)B * h->K * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  EDGL_CUDA(cudaMemcpyAsync(val_host, h->st_val, (size_t)B * h->K * sizeof(float), cudaMemcpyDeviceToHost, st));
+  EDGL_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int edgl_logits_topk(edgl_handle* h, const float* y, const int64_t* seen_ids, int seen_len, int Bt,
+                     int32_t* cand_idx, float* cand_val, void* stream) {
+  EDGL_TRY(check_ready(h, Bt, false));
+  if (!y || !cand_idx || !cand_val) return set_error(EDGL_EINVAL, "null argument");
+  EDGL_REQUIRE(!seen_ids || seen_len >= 1, "seen_len must be >= 1");
+  return logits_topk(h, y, seen_ids, seen_len, Bt, cand_idx, cand_val, (cudaStream_t)stream);
+}
+
+int edgl_topk_merge(const float* cand_val, const int32_t* cand_idx, int G, int Bt, int K, int32_t* idx, float* val,
+                    void* stream) {
+  if (!cand_val || !cand_idx || !idx || !val) return set_error(EDGL_EINVAL, "null argument");
+  EDGL_REQUIRE(Bt >= 0, "negative batch");
+  return launch_topk_merge(cand_val, cand_idx, G, Bt, K, idx, val, (cudaStream_t)stream);
+}
+
+int edgl_time_sinusoid_code(const float* ts, int B, int L, int d, float* out, void* stream) {
+  if (!ts || !out) return set_error(EDGL_EINVAL, "null argument");
+  EDGL_REQUIRE(B >= 0 && L >= 0 && d >= 2 && d % 2 == 0, "time_sinusoid_code: bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  std::vector<float> sc(d / 2);
+  for (int j = 0; j < d / 2; ++j) sc[j] = (float)pow(10000.0, (double)(2 * j) * 1.0 / (double)d);
+  float* dsc = nullptr;
+  EDGL_CUDA(cudaMallocAsync(&dsc, sc.size() * sizeof(float), st));
+  EDGL_CUDA(cudaMemcpyAsync(dsc, sc.data(), sc.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+  int rc = launch_time_code(ts, dsc, (long long)B * L, d, out, st);
+  cudaFreeAsync(dsc, st);
+  EDGL_CUDA(cudaStreamSynchronize(st));
+  return rc;
+}
+
+int edgl_embedding_lookup(const float* table, int vocab, int d, int zero_pad, int scale, const int64_t* ids,
+                          int64_t n_ids, float* out, void* stream) {
+  if (!table || !ids || !out) return set_error(EDGL_EINVAL, "null argument");
+  EDGL_REQUIRE(vocab >= 1 && d >= 1 && n_ids >= 0, "embedding_lookup: bad shape");
+  const float s = scale ? (float)sqrt((double)d) : 1.0f;  // coding.py:62-63
+  return launch_lookup(table, vocab, d, zero_pad, s, ids, n_ids, out, (cudaStream_t)stream);
+}
+
+int edgl_embed(edgl_handle* h, const int64_t* seqs_i, const float* seqs_t, int B, float* X0, float* spans,
+               uint8_t* marks, void* stream) {
+  EDGL_TRY(check_ready(h, B, false));
+  if (!seqs_i || !seqs_t) return set_error(EDGL_EINVAL, "null argument");
+  EmbedArgs e = embed_args(h, seqs_i, seqs_t, B);
+  e.X0 = X0;
+  e.ldx0 = (h->cfg.model == EDGL_MODEL_EASYDGL ? 3 : 2) * h->d;
+  e.spans = spans;
+  e.marks = marks;
+  return launch_embed(e, (cudaStream_t)stream);
+}
+
+int edgl_attention_layer(edgl_handle* h, int block, const float* queries, int Cq, const float* keys, int Ck,
+                         const uint8_t* kmask, const float* intervals, const uint8_t* marks, int B, int causality,
+                         float* out, float* lam, void* stream) {
+  EDGL_TRY(check_ready(h, B));
+  if (!queries || !kmask || !intervals || !marks || !out) return set_error(EDGL_EINVAL, "null argument");
+  EDGL_REQUIRE(block >= 0 && block < h->cfg.num_blocks, "block %d out of range", block);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int d = h->d;
+  const long long rows = (long long)B * h->L;
+  const auto& w = h->bt[block];
+  const int cin = cin_of(h, block);
+  EDGL_REQUIRE(Cq == cin, "queries width %d does not match the block's dense kernel (%d)", Cq, cin);
+  if (h->cfg.model == EDGL_MODEL_EASYDGL) {
+    // BiMAU: `keys` and `causality` are ignored by the reference (temporal.py:404-429, Q15)
+    EDGL_TRY(dense(queries, Cq, F(w, "qkvt_w"), 4 * d, F(w, "qkvt_b"), h->qkvt, 4 * d, rows, 4 * d, Cq, ACT_NONE,
+                   nullptr, 0, st));
+    AttnArgs a = attn_args(h, w, h->qkvt, kmask, intervals, marks, queries, Cq, out, lam, B, false, true);
+    return launch_attention(a, st);
+  }
+  if (!keys) return set_error(EDGL_EINVAL, "MAU needs keys");
+  EDGL_REQUIRE(Ck == cin, "keys width %d does not match the block's dense kernels (%d)", Ck, cin);
+  EDGL_TRY(dense(queries, Cq, F(w, "q_w"), d, F(w, "q_b"), h->qkvt, 4 * d, rows, d, Cq, ACT_NONE, nullptr, 0, st));
+  EDGL_TRY(dense(keys, Ck, h->wkvt[block], 3 * d, h->bkvt[block], h->qkvt + d, 4 * d, rows, 3 * d, Ck, ACT_NONE,
+                 nullptr, 0, st));
+  AttnArgs a = attn_args(h, w, h->qkvt, kmask, intervals, marks, queries, Cq, out, lam, B, causality != 0, false);
+  return launch_attention(a, st);
+}
+
+int edgl_intensity(edgl_handle* h, int block, const float* H, const float* intervals, const uint8_t* marks, int B,
+                   float* G, float* lam, void* stream) {
+  EDGL_TRY(check_ready(h, B, false));
+  if (!H || !intervals || !marks) return set_error(EDGL_EINVAL, "null argument");
+  EDGL_REQUIRE(block >= 0 && block < h->cfg.num_blocks, "block %d out of range", block);
+  const auto& w = h->bt[block];
+  return launch_intensity(H, intervals, marks, F(w, "int_w"), F(w, "int_b"), F(w, "int_weight"), F(w, "int_scaling"),
+                          B, h->L, h->h, h->dh, h->E, G, lam, (cudaStream_t)stream);
+}
+
+int edgl_layernorm(const float* x, const float* gamma, const float* beta, int B, int L, int C, float* out,
+                   void* stream) {
+  if (!x || !gamma || !beta || !out) return set_error(EDGL_EINVAL, "null argument");
+  EDGL_REQUIRE(B >= 0 && L >= 1 && C >= 1, "layernorm: bad shape");
+  return launch_layernorm(x, gamma, beta, B, L, C, out, false, (cudaStream_t)stream);
+}
+
+int edgl_dense(const float* x, const float* w, const float* b, int M, int K, int N, int act, float* out,
+               void* stream) {
+  if (!x || !w || !out) return set_error(EDGL_EINVAL, "null argument");
+  EDGL_REQUIRE(act >= 0 && act <= 2, "dense: unknown activation %d", act);
+  return dense(x, K, w, N, b, out, N, M, N, K, act, nullptr, 0, (cudaStream_t)stream);
+}
+
+int edgl_topk(float* logits, int B, int N, const int64_t* seen_ids, int seen_len, int K, int32_t* idx, float* val,
+              void* stream) {
+  if (!logits || !idx || !val) return set_error(EDGL_EINVAL, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (seen_ids) EDGL_TRY(launch_mask_seen(logits, N, B, seen_ids, seen_len, 0, N, st));
+  return launch_topk(logits, N, B, N, K, 0, idx, val, st);
+}
+
+}  // extern "C"

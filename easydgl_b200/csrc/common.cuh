@@ -1,0 +1,121 @@
+// common.cuh - shared helpers for libeasydgl_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <atomic>
+#include <string>
+
+namespace edgl {
+
+// thread-local last error message (edgl_last_error)
+std::string& last_error();
+int set_error(int code, const char* fmt, ...);
+
+extern std::atomic<long long> g_launches;
+inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+#define EDGL_CUDA(expr)                                                                          \
+  do {                                                                                           \
+    cudaError_t _e = (expr);                                                                     \
+    if (_e != cudaSuccess)                                                                       \
+      return ::edgl::set_error(-3, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                               __LINE__);                                                        \
+  } while (0)
+
+#define EDGL_LAUNCH_CHECK()                                                                      \
+  do {                                                                                           \
+    ::edgl::count_launch();                                                                      \
+    cudaError_t _e = cudaGetLastError();                                                         \
+    if (_e != cudaSuccess)                                                                       \
+      return ::edgl::set_error(-3, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e),    \
+                               __FILE__, __LINE__);                                              \
+  } while (0)
+
+#define EDGL_REQUIRE(cond, ...)                                  \
+  do {                                                           \
+    if (!(cond)) return ::edgl::set_error(-1, __VA_ARGS__);      \
+  } while (0)
+
+#define EDGL_TRY(expr)          \
+  do {                          \
+    int _r = (expr);            \
+    if (_r != 0) return _r;     \
+  } while (0)
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ------------------------------------------------------------------ kernel launchers (one per .cu)
+enum Act { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2 };
+
+// C[M,N] (ldc) = act(A[M,K] (lda) @ W + bias[N] + pbias[(m % pperiod), N]) + R[M,N] (ldr)
+// W is [K,N] (ldw) row-major, or, if w_is_nk, [N,K] (ldw) row-major (C = A @ W^T).
+// col0_const: if non-null-flag set, global column (col_offset+0)==0 gets exactly bias (acc ignored)
+struct GemmArgs {
+  const float* A = nullptr; int lda = 0;
+  const float* W = nullptr; int ldw = 0; bool w_is_nk = false;
+  float* C = nullptr; int ldc = 0;
+  int M = 0, N = 0, K = 0;
+  const float* bias = nullptr;                 // [N] or null
+  const float* pbias = nullptr; int pperiod = 0;  // [pperiod, N] or null
+  const float* R = nullptr; int ldr = 0;       // residual or null
+  int act = ACT_NONE;
+  bool zero_wrow0 = false;  // w_is_nk only: treat W row 0 (= output column 0) as all-zero (zero_pad table)
+};
+int launch_gemm(const GemmArgs& a, cudaStream_t st);
+
+struct EmbedArgs {
+  int model;  // 0 EasyDGL, 1 CTSMA
+  const int64_t* ids; const float* ts; int B, L, ts_len, d, E;
+  float time_scale; int64_t mask_id;
+  const float* item_table; int num_rows;       // raw variable, row 0 treated as zero
+  const float* pos_table;                      // [L,d]
+  const float* mark_embs;                      // [E,d] raw (row 0 treated as zero); EasyDGL only
+  const uint8_t* mark_table8; int mark_rows;   // [mark_rows,E]
+  const float* tscale;                         // [d/2] sinusoid scales (fp32)
+  // outputs (any may be null)
+  float* X0; int ldx0;                         // full concat [B*L, 3d | 2d]
+  float* Xa; int ldxa;                         // fused input: [x+tcode | mark-count histogram] (EasyDGL), width d+E
+  float* spans;                                // [B*L]
+  uint8_t* marks;                              // [B*L,E]
+  uint8_t* kmask;                              // [B*L]
+};
+int launch_embed(const EmbedArgs& a, cudaStream_t st);
+int launch_time_code(const float* ts, const float* tscale, long long rows, int d, float* out, cudaStream_t st);
+int launch_lookup(const float* table, int vocab, int d, int zero_pad, float scale, const int64_t* ids,
+                  long long n, float* out, cudaStream_t st);
+int launch_mark_table_to_u8(const int64_t* src, long long n, uint8_t* dst, int* err_flag, int E, cudaStream_t st);
+
+struct AttnArgs {
+  const float* Q; int ldq;   // [B*L, >=d] Q columns start at Q
+  const float* K; int ldk;
+  const float* V; int ldv;
+  const float* T; int ldt;
+  const uint8_t* kmask;      // [B*L]
+  const float* spans;        // [B*L]
+  const uint8_t* marks;      // [B*L,E]
+  const float* R; int ldr;   // residual (first d columns) or null
+  const float* int_w; const float* int_b; const float* int_weight; const float* int_scaling;
+  float* O; int ldo;         // [B*L, d]
+  float* lam;                // [h*B, L, E] or null
+  int B, L, d, h, E;
+  bool causal, diag_one;
+};
+int launch_attention(const AttnArgs& a, cudaStream_t st);
+int launch_intensity(const float* H, const float* spans, const uint8_t* marks, const float* int_w,
+                     const float* int_b, const float* int_weight, const float* int_scaling, int B, int L,
+                     int h, int dh, int E, float* G, float* lam, cudaStream_t st);
+
+// LayerNorm over (L,C) jointly per sample. last_only: write only row L-1 to out [B,C].
+int launch_layernorm(const float* x, const float* gamma, const float* beta, int B, int L, int C, float* out,
+                     bool last_only, cudaStream_t st);
+
+int launch_mask_seen(float* logits, int ld, int B, const int64_t* ids, int seen_len, long long col0,
+                     long long col1, cudaStream_t st);
+int launch_topk(const float* logits, int ld, int B, int N, int K, int col_offset, int32_t* idx, float* val,
+                cudaStream_t st);
+int launch_topk_merge(const float* cand_val, const int32_t* cand_idx, int G, int Bt, int K, int32_t* idx,
+                      float* val, cudaStream_t st);
+
+}  // namespace edgl

@@ -1,0 +1,93 @@
+// norm.cu - Base.layernorm (Base.py:12-67).
+// begin_norm_axis=1: mean / population variance over (L,C) JOINTLY per sample (Base.py:51-52, Q2),
+// eps 1e-12, gamma/beta over the last axis, tf.nn.batch_normalization form
+//   out = x * inv + (beta - mean * inv),  inv = rsqrt(var + eps) * gamma   (Base.py:57-63).
+// One CTA per sequence; the sample is cached in shared memory when it fits so HBM sees one read and
+// one write per element; two-pass (mean, then squared deviations) like tf.nn.moments.
+#include "common.cuh"
+
+namespace edgl {
+
+__device__ __forceinline__ float block_sum_256(float v, float* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();  // protect red[] reuse
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  float t = (lane < 8) ? red[lane] : 0.f;
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  return __shfl_sync(0xffffffffu, t, 0);
+}
+
+template <bool CACHE>
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, int L, int C,
+                                                        float* __restrict__ out, int last_only) {
+  extern __shared__ __align__(16) float xs[];
+  __shared__ float red[8];
+  const long long n = (long long)L * C;
+  const float* xp = x + (long long)blockIdx.x * n;
+  const int n4 = (int)(n >> 2);  // n % 4 == 0 is guaranteed by the launcher
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n4; i += 256) {
+    const float4 v = reinterpret_cast<const float4*>(xp)[i];
+    if (CACHE) reinterpret_cast<float4*>(xs)[i] = v;
+    s += (v.x + v.y) + (v.z + v.w);
+  }
+  const float mean = block_sum_256(s, red) / (float)n;
+  float q = 0.f;
+  for (int i = threadIdx.x; i < n4; i += 256) {
+    const float4 v = CACHE ? reinterpret_cast<const float4*>(xs)[i] : reinterpret_cast<const float4*>(xp)[i];
+    const float a = v.x - mean, b = v.y - mean, c = v.z - mean, d = v.w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+  const float var = block_sum_256(q, red) / (float)n;
+  const float rstd = __frcp_rn(sqrtf(var + 1e-12f));
+  if (last_only) {
+    const float* src = (CACHE ? xs : xp) + (long long)(L - 1) * C;
+    float* op = out + (long long)blockIdx.x * C;
+    for (int c = threadIdx.x; c < C; c += 256) {
+      const float inv = rstd * gamma[c];
+      op[c] = src[c] * inv + (beta[c] - mean * inv);
+    }
+  } else {
+    float* op = out + (long long)blockIdx.x * n;
+    const int c4n = C >> 2;
+    for (int i = threadIdx.x; i < n4; i += 256) {
+      const float4 v = CACHE ? reinterpret_cast<const float4*>(xs)[i] : reinterpret_cast<const float4*>(xp)[i];
+      const int c = (i % c4n) * 4;
+      const float4 g = *reinterpret_cast<const float4*>(gamma + c);
+      const float4 bt = *reinterpret_cast<const float4*>(beta + c);
+      float4 o;
+      float inv;
+      inv = rstd * g.x; o.x = v.x * inv + (bt.x - mean * inv);
+      inv = rstd * g.y; o.y = v.y * inv + (bt.y - mean * inv);
+      inv = rstd * g.z; o.z = v.z * inv + (bt.z - mean * inv);
+      inv = rstd * g.w; o.w = v.w * inv + (bt.w - mean * inv);
+      reinterpret_cast<float4*>(op)[i] = o;
+    }
+  }
+}
+
+int launch_layernorm(const float* x, const float* gamma, const float* beta, int B, int L, int C, float* out,
+                     bool last_only, cudaStream_t st) {
+  EDGL_REQUIRE(C % 4 == 0, "layernorm: channel count must be a multiple of 4 (got %d)", C);
+  EDGL_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(gamma) & 15) == 0 && (reinterpret_cast<uintptr_t>(beta) & 15) == 0,
+               "layernorm: pointers must be 16-byte aligned");
+  if (B == 0) return 0;
+  const size_t bytes = (size_t)L * C * sizeof(float);
+  if (bytes <= 200 * 1024) {
+    auto kern = layernorm_kernel<true>;
+    EDGL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    kern<<<B, 256, bytes, st>>>(x, gamma, beta, L, C, out, last_only ? 1 : 0);
+  } else {
+    layernorm_kernel<false><<<B, 256, 0, st>>>(x, gamma, beta, L, C, out, last_only ? 1 : 0);
+  }
+  EDGL_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace edgl

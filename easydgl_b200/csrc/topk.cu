@@ -1,0 +1,227 @@
+// topk.cu - ranking part of Sequential.eval (Base.py:150-181).
+//   mask_seen : logits[b, seqs_i[b,l]] = -inf for every l (Base.py:156-163; adding -inf to a finite logit)
+//   topk      : tf.nn.top_k(., k) - sorted descending, ties -> LOWER index first (Base.py:181)
+//   merge     : K-way merge of per-shard candidate lists (multi-GPU)
+// Ranking is done on the masked logits: softmax (Base.py:164) is monotone, so the order is the same
+// wherever fp32 softmax is injective (DESIGN.md discusses the underflow corner).
+// Integer/index work: bit-exact by construction (order-preserving uint keys, radix select, ties by index).
+#include "common.cuh"
+
+namespace edgl {
+
+__device__ __forceinline__ uint32_t f2key(float f) {
+  uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key2f(uint32_t k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+__device__ __forceinline__ unsigned long long compose(uint32_t key, uint32_t idx) {
+  return ((unsigned long long)key << 32) | (unsigned long long)(0xffffffffu - idx);
+}
+
+__global__ void mask_seen_kernel(float* __restrict__ logits, int ld, long long n, int seen_len,
+                                 const int64_t* __restrict__ ids, long long col0, long long col1) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long long b = i / seen_len;
+  const long long id = ids[i];
+  if (id >= col0 && id < col1) logits[b * ld + (id - col0)] = -INFINITY;
+}
+
+int launch_mask_seen(float* logits, int ld, int B, const int64_t* ids, int seen_len, long long col0,
+                     long long col1, cudaStream_t st) {
+  const long long n = (long long)B * seen_len;
+  if (n == 0) return 0;
+  mask_seen_kernel<<<cdiv(n, 256), 256, 0, st>>>(logits, ld, n, seen_len, ids, col0, col1);
+  EDGL_LAUNCH_CHECK();
+  return 0;
+}
+
+// descending bitonic sort of n (power of two) u64 in shared memory, blockDim.x threads
+__device__ void bitonic_desc(unsigned long long* s, int n) {
+  for (int k = 2; k <= n; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      __syncthreads();
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const unsigned long long a = s[i], b = s[ixj];
+          const bool desc = (i & k) == 0;
+          if (desc ? (a < b) : (a > b)) {
+            s[i] = b;
+            s[ixj] = a;
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// One CTA (256 threads) per row.  dynamic smem: KP u64 candidates.
+__global__ void __launch_bounds__(256) topk_kernel(const float* __restrict__ logits, int ld, int N, int K, int KP,
+                                                   int col_offset, int32_t* __restrict__ idx_out,
+                                                   float* __restrict__ val_out) {
+  extern __shared__ __align__(16) unsigned long long cand[];
+  __shared__ unsigned int hist[256];
+  __shared__ unsigned int s_prefix, s_remaining, s_eq_total, s_gt_cnt, s_eq_cnt;
+  __shared__ unsigned int warp_tot[8];
+  const float* p = logits + (long long)blockIdx.x * ld;
+  const int tid = threadIdx.x;
+  const int Keff = K < N ? K : N;
+
+  if (tid == 0) {
+    s_prefix = 0;
+    s_remaining = Keff;
+    s_gt_cnt = 0;
+    s_eq_cnt = 0;
+  }
+  for (int i = tid; i < KP; i += 256) cand[i] = 0ull;
+  uint32_t mask = 0;
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 24 - 8 * pass;
+    hist[tid] = 0;
+    __syncthreads();
+    const uint32_t prefix = s_prefix;
+    for (int i = tid; i < N; i += 256) {
+      const uint32_t key = f2key(p[i]);
+      if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      unsigned int cum = 0, rem = s_remaining;
+      int dgt = 255;
+      for (; dgt > 0; --dgt) {
+        if (cum + hist[dgt] >= rem) break;
+        cum += hist[dgt];
+      }
+      s_remaining = rem - cum;       // how many still to take among keys with this digit
+      s_eq_total = hist[dgt];
+      s_prefix = prefix | ((uint32_t)dgt << shift);
+    }
+    mask |= 0xffu << shift;
+    __syncthreads();
+  }
+  const uint32_t T = s_prefix;              // the Keff-th largest key
+  const unsigned int need_eq = s_remaining; // ties at T to keep (lowest indices first)
+  const unsigned int n_gt = Keff - need_eq;
+  const bool all_eq = (s_eq_total == need_eq);
+  __syncthreads();
+
+  if (all_eq) {
+    for (int i = tid; i < N; i += 256) {
+      const uint32_t key = f2key(p[i]);
+      if (key >= T) {
+        const unsigned int pos = atomicAdd(&s_gt_cnt, 1u);
+        cand[pos] = compose(key, (uint32_t)i);
+      }
+    }
+  } else {
+    // ordered pass: ties must be taken in index order
+    unsigned int eq_taken = 0;
+    for (int base = 0; base < N && eq_taken < need_eq; base += 256) {
+      const int i = base + tid;
+      uint32_t key = 0;
+      if (i < N) key = f2key(p[i]);
+      const bool is_eq = (i < N) && key == T;
+      const unsigned int bal = __ballot_sync(0xffffffffu, is_eq);
+      const int lane = tid & 31, w = tid >> 5;
+      if (lane == 0) warp_tot[w] = __popc(bal);
+      __syncthreads();
+      unsigned int before = 0, total = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (j < w) before += warp_tot[j];
+        total += warp_tot[j];
+      }
+      if (is_eq) {
+        const unsigned int pos = eq_taken + before + __popc(bal & ((1u << lane) - 1u));
+        if (pos < need_eq) cand[n_gt + pos] = compose(key, (uint32_t)i);
+      }
+      eq_taken += total;
+      __syncthreads();
+    }
+    for (int i = tid; i < N; i += 256) {
+      const uint32_t key = f2key(p[i]);
+      if (key > T) {
+        const unsigned int pos = atomicAdd(&s_gt_cnt, 1u);
+        cand[pos] = compose(key, (uint32_t)i);
+      }
+    }
+  }
+  bitonic_desc(cand, KP);
+  for (int i = tid; i < K; i += 256) {
+    const long long o = (long long)blockIdx.x * K + i;
+    if (i < Keff) {
+      const unsigned long long c = cand[i];
+      idx_out[o] = (int32_t)(0xffffffffu - (uint32_t)(c & 0xffffffffull)) + col_offset;
+      val_out[o] = key2f((uint32_t)(c >> 32));
+    } else {  // fewer than K columns: pad
+      idx_out[o] = -1;
+      val_out[o] = -INFINITY;
+    }
+  }
+}
+
+static int next_pow2(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+int launch_topk(const float* logits, int ld, int B, int N, int K, int col_offset, int32_t* idx, float* val,
+                cudaStream_t st) {
+  EDGL_REQUIRE(K >= 1 && K <= 2048, "topk: K must be in [1,2048] (got %d)", K);
+  EDGL_REQUIRE(N >= 1, "topk: N must be >= 1");
+  if (B == 0) return 0;
+  const int KP = next_pow2(K);
+  topk_kernel<<<B, 256, (size_t)KP * 8, st>>>(logits, ld, N, K, KP, col_offset, idx, val);
+  EDGL_LAUNCH_CHECK();
+  return 0;
+}
+
+// merge: cand_* are [G][Bt][K]; entries with idx < 0 are padding.
+__global__ void __launch_bounds__(256) topk_merge_kernel(const float* __restrict__ cv, const int32_t* __restrict__ ci,
+                                                         int G, int Bt, int K, int KP, int32_t* __restrict__ idx_out,
+                                                         float* __restrict__ val_out) {
+  extern __shared__ __align__(16) unsigned long long cand[];
+  const int row = blockIdx.x;
+  for (int i = threadIdx.x; i < KP; i += 256) {
+    unsigned long long c = 0ull;
+    if (i < G * K) {
+      const int g = i / K, j = i % K;
+      const long long o = ((long long)g * Bt + row) * K + j;
+      const int32_t id = ci[o];
+      if (id >= 0) c = compose(f2key(cv[o]), (uint32_t)id);
+    }
+    cand[i] = c;
+  }
+  bitonic_desc(cand, KP);
+  for (int i = threadIdx.x; i < K; i += 256) {
+    const unsigned long long c = cand[i];
+    const long long o = (long long)row * K + i;
+    if (c != 0ull) {
+      idx_out[o] = (int32_t)(0xffffffffu - (uint32_t)(c & 0xffffffffull));
+      val_out[o] = key2f((uint32_t)(c >> 32));
+    } else {
+      idx_out[o] = -1;
+      val_out[o] = -INFINITY;
+    }
+  }
+}
+
+int launch_topk_merge(const float* cand_val, const int32_t* cand_idx, int G, int Bt, int K, int32_t* idx,
+                      float* val, cudaStream_t st) {
+  EDGL_REQUIRE(G >= 1 && K >= 1 && (long long)G * K <= 16384, "topk_merge: G*K must be <= 16384");
+  if (Bt == 0) return 0;
+  const int KP = next_pow2(G * K);
+  auto kern = topk_merge_kernel;
+  const size_t smem = (size_t)KP * 8;
+  if (smem > 48 * 1024) EDGL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<Bt, 256, smem, st>>>(cand_val, cand_idx, G, Bt, K, KP, idx, val);
+  EDGL_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace edgl

@@ -1,0 +1,301 @@
+"""Thin host-side owner of one ``edgl_handle`` (include/easydgl_b200.h).
+
+PyTorch tensors are containers only: this class allocates them, passes
+``data_ptr()`` + the current CUDA stream to the C ABI, and keeps the weight tensors
+alive (the library borrows them).  No arithmetic happens here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import EdglConfig, check
+
+_MODEL_ID = {"EasyDGL": _lib.EDGL_MODEL_EASYDGL, "CTSMA": _lib.EDGL_MODEL_CTSMA}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _req(t: torch.Tensor, dtype, name: str, device=None) -> torch.Tensor:
+    if not torch.is_tensor(t):
+        raise ValueError("%s must be a torch tensor" % name)
+    if t.dtype != dtype:
+        raise ValueError("%s must be %s (got %s)" % (name, dtype, t.dtype))
+    if device is not None and t.device != device:
+        raise ValueError("%s must live on %s (got %s)" % (name, device, t.device))
+    return t.contiguous()
+
+
+class Engine:
+    """One model instance on one GPU.  ``cfg`` is a FLAGS-like namespace produced by
+    ``easydgl_b200.synth.make_config`` (or the facade models); ``weights`` the nested
+    dict of SURVEY.md 8(a-params) names."""
+
+    def __init__(self, cfg, weights: Dict, max_batch: int, device="cuda:0", shard_rank: int = 0,
+                 shard_world: int = 1, topk: Optional[int] = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("easydgl_b200 needs a CUDA device (sm_100a); there is no CPU path")
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        self.cfg = cfg
+        self.K = int(topk if topk is not None else getattr(cfg, "topk", 100))
+        self.L, self.d, self.h, self.E = cfg.L, cfg.num_units, cfg.num_heads, cfg.num_events
+        self.ts_len = cfg.ts_len
+        self.N1 = cfg.num_rows
+        self.max_batch = int(max_batch)
+        self.shard_rank, self.shard_world = shard_rank, shard_world
+        per = (self.N1 + shard_world - 1) // shard_world
+        self.c0 = min(per * shard_rank, self.N1)
+        self.c1 = min(self.c0 + per, self.N1)
+        self._handle = C.c_void_p()
+        self._w = {}
+        mark_rows = int(weights["mark_table"].shape[0])
+        c = EdglConfig(model=_MODEL_ID[cfg.model], max_batch=self.max_batch, seq_len=self.L, num_units=self.d,
+                       num_heads=self.h, num_blocks=cfg.num_blocks, num_events=self.E, num_rows=self.N1,
+                       mark_rows=mark_rows, topk=self.K, time_scale=float(cfg.time_scale),
+                       mask_id=int(cfg.mask_id), shard_rank=shard_rank, shard_world=shard_world)
+        with torch.cuda.device(self.device):
+            check(self.lib.edgl_create(C.byref(c), C.byref(self._handle)))
+        self.load_weights(weights)
+
+    # ------------------------------------------------------------------ weights
+    def load_weights(self, weights: Dict):
+        with torch.cuda.device(self.device):
+            for name, v in weights.items():
+                if name == "blocks":
+                    for i, blk in enumerate(v):
+                        for n2, t in blk.items():
+                            self._bind(n2, i, t)
+                else:
+                    self._bind(name, -1, v)
+            check(self.lib.edgl_commit(self._handle, _stream()))
+
+    def _bind(self, name: str, block: int, t: torch.Tensor):
+        dt = torch.int64 if name == "mark_table" else torch.float32
+        t = t.detach().to(device=self.device, dtype=dt).contiguous()
+        self._w[(name, block)] = t  # borrowed by the library: keep alive
+        check(self.lib.edgl_set_tensor(self._handle, name.encode(), block, t.data_ptr(), t.numel()))
+
+    def close(self):
+        if self._handle:
+            self.lib.edgl_destroy(self._handle)
+            self._handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ model-level
+    def _inputs(self, seqs_i, seqs_t) -> Tuple[torch.Tensor, torch.Tensor, int]:
+        seqs_i = _req(seqs_i, torch.int64, "seqs_i", self.device)
+        seqs_t = _req(seqs_t, torch.float32, "seqs_t", self.device)
+        if seqs_i.dim() != 2 or seqs_i.shape[1] != self.L:
+            raise ValueError("seqs_i must be [B,%d] (got %s)" % (self.L, tuple(seqs_i.shape)))
+        if seqs_t.dim() != 2:
+            raise AssertionError("the tensor rank should be 2.")  # coding.py:139
+        if seqs_t.shape != (seqs_i.shape[0], self.ts_len):
+            raise ValueError("seqs_t must be [B,%d] (got %s)" % (self.ts_len, tuple(seqs_t.shape)))
+        return seqs_i, seqs_t, int(seqs_i.shape[0])
+
+    def forward_logits(self, seqs_i, seqs_t) -> torch.Tensor:
+        seqs_i, seqs_t, B = self._inputs(seqs_i, seqs_t)
+        out = torch.empty((B, self.c1 - self.c0), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.edgl_forward_logits(self._handle, seqs_i.data_ptr(), seqs_t.data_ptr(), B,
+                                               out.data_ptr(), _stream()))
+        return out
+
+    def forward_topk(self, seqs_i, seqs_t, mask_seen: bool = True, out=None):
+        seqs_i, seqs_t, B = self._inputs(seqs_i, seqs_t)
+        if out is None:
+            idx = torch.empty((B, self.K), dtype=torch.int32, device=self.device)
+            val = torch.empty((B, self.K), dtype=torch.float32, device=self.device)
+        else:
+            idx, val = out
+        with torch.cuda.device(self.device):
+            check(self.lib.edgl_forward_topk(self._handle, seqs_i.data_ptr(), seqs_t.data_ptr(), B,
+                                             int(bool(mask_seen)), idx.data_ptr(), val.data_ptr(), _stream()))
+        return idx, val
+
+    def forward_topk_host(self, seqs_i_cpu, seqs_t_cpu, idx_cpu, val_cpu, mask_seen: bool = True):
+        """End-to-end call on HOST buffers (ideally pinned): H2D, forward, top-K, D2H, sync."""
+        B = int(seqs_i_cpu.shape[0])
+        for t in (seqs_i_cpu, seqs_t_cpu, idx_cpu, val_cpu):
+            if t.device.type != "cpu" or not t.is_contiguous():
+                raise ValueError("forward_topk_host takes contiguous CPU tensors")
+        if seqs_i_cpu.dtype != torch.int64 or seqs_t_cpu.dtype != torch.float32:
+            raise ValueError("seqs_i must be int64 and seqs_t float32")
+        if idx_cpu.dtype != torch.int32 or val_cpu.dtype != torch.float32:
+            raise ValueError("idx must be int32 and val float32")
+        if tuple(seqs_i_cpu.shape) != (B, self.L) or tuple(seqs_t_cpu.shape) != (B, self.ts_len):
+            raise ValueError("bad input shapes")
+        if idx_cpu.numel() < B * self.K or val_cpu.numel() < B * self.K:
+            raise ValueError("output buffers too small")
+        with torch.cuda.device(self.device):
+            check(self.lib.edgl_forward_topk_host(self._handle, seqs_i_cpu.data_ptr(), seqs_t_cpu.data_ptr(), B,
+                                                  int(bool(mask_seen)), idx_cpu.data_ptr(), val_cpu.data_ptr(),
+                                                  _stream()))
+        return idx_cpu, val_cpu
+
+    def encode(self, seqs_i, seqs_t) -> torch.Tensor:
+        seqs_i, seqs_t, B = self._inputs(seqs_i, seqs_t)
+        y = torch.empty((B, self.d), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.edgl_encode(self._handle, seqs_i.data_ptr(), seqs_t.data_ptr(), B, y.data_ptr(), _stream()))
+        return y
+
+    def logits_topk(self, y, seen_ids=None):
+        """Local top-K of this handle's item shard for rows ``y`` [Bt,d]; global column ids."""
+        y = _req(y, torch.float32, "y", self.device)
+        Bt = int(y.shape[0])
+        seen_len = 0
+        if seen_ids is not None:
+            seen_ids = _req(seen_ids, torch.int64, "seen_ids", self.device)
+            seen_len = int(seen_ids.shape[1])
+        idx = torch.empty((Bt, self.K), dtype=torch.int32, device=self.device)
+        val = torch.empty((Bt, self.K), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.edgl_logits_topk(self._handle, y.data_ptr(), _ptr(seen_ids), seen_len, Bt,
+                                            idx.data_ptr(), val.data_ptr(), _stream()))
+        return idx, val
+
+    # ------------------------------------------------------------------ layer-level
+    def embed(self, seqs_i, seqs_t):
+        seqs_i, seqs_t, B = self._inputs(seqs_i, seqs_t)
+        width = (3 if self.cfg.model == "EasyDGL" else 2) * self.d
+        X0 = torch.empty((B, self.L, width), dtype=torch.float32, device=self.device)
+        spans = torch.empty((B, self.L), dtype=torch.float32, device=self.device)
+        marks = torch.empty((B, self.L, self.E), dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.edgl_embed(self._handle, seqs_i.data_ptr(), seqs_t.data_ptr(), B, X0.data_ptr(),
+                                      spans.data_ptr(), marks.data_ptr(), _stream()))
+        return X0, spans, marks
+
+    def attention_layer(self, block, queries, keys, kmask, intervals, marks, causality=False, want_lam=True):
+        queries = _req(queries, torch.float32, "queries", self.device)
+        B, L, Cq = queries.shape
+        if L != self.L:
+            raise ValueError("queries must be [B,%d,C]" % self.L)
+        keys_c = None if keys is None else _req(keys, torch.float32, "keys", self.device)
+        kmask = _req(kmask, torch.uint8, "kmask", self.device)
+        intervals = _req(intervals, torch.float32, "intervals", self.device)
+        marks = _req(marks, torch.uint8, "marks", self.device)
+        out = torch.empty((B, L, self.d), dtype=torch.float32, device=self.device)
+        lam = torch.empty((self.h * B, L, self.E), dtype=torch.float32, device=self.device) if want_lam else None
+        with torch.cuda.device(self.device):
+            check(self.lib.edgl_attention_layer(self._handle, block, queries.data_ptr(), Cq, _ptr(keys_c),
+                                                0 if keys_c is None else keys_c.shape[2], kmask.data_ptr(),
+                                                intervals.data_ptr(), marks.data_ptr(), B, int(bool(causality)),
+                                                out.data_ptr(), _ptr(lam), _stream()))
+        return out, lam
+
+    def intensity(self, block, H, intervals, marks):
+        H = _req(H, torch.float32, "H", self.device)
+        intervals = _req(intervals, torch.float32, "intervals", self.device)
+        marks = _req(marks, torch.uint8, "marks", self.device)
+        hB, L, dh = H.shape
+        B = hB // self.h
+        G = torch.empty((hB, L, L), dtype=torch.float32, device=self.device)
+        lam = torch.empty((hB, L, self.E), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.edgl_intensity(self._handle, block, H.data_ptr(), intervals.data_ptr(), marks.data_ptr(),
+                                          B, G.data_ptr(), lam.data_ptr(), _stream()))
+        return G, lam
+
+
+# ---------------------------------------------------------------------- handle-free ops
+def topk_merge(cand_val: torch.Tensor, cand_idx: torch.Tensor):
+    """[G,Bt,K] per-shard candidates -> merged (idx [Bt,K] int32, val [Bt,K]); ties -> lower id."""
+    lib = _lib.load()
+    cand_val = _req(cand_val, torch.float32, "cand_val")
+    cand_idx = _req(cand_idx, torch.int32, "cand_idx")
+    G, Bt, K = cand_val.shape
+    idx = torch.empty((Bt, K), dtype=torch.int32, device=cand_val.device)
+    val = torch.empty((Bt, K), dtype=torch.float32, device=cand_val.device)
+    with torch.cuda.device(cand_val.device):
+        check(lib.edgl_topk_merge(cand_val.data_ptr(), cand_idx.data_ptr(), G, Bt, K, idx.data_ptr(), val.data_ptr(),
+                                  _stream()))
+    return idx, val
+
+
+def time_sinusoid_code(ts: torch.Tensor, num_units: int) -> torch.Tensor:
+    lib = _lib.load()
+    if ts.dim() != 2:
+        raise AssertionError("the tensor rank should be 2.")  # coding.py:139
+    ts = _req(ts, torch.float32, "ts")
+    B, L = ts.shape
+    out = torch.empty((B, L, num_units), dtype=torch.float32, device=ts.device)
+    with torch.cuda.device(ts.device):
+        check(lib.edgl_time_sinusoid_code(ts.data_ptr(), B, L, num_units, out.data_ptr(), _stream()))
+    return out
+
+
+def embedding_lookup(table: torch.Tensor, ids: torch.Tensor, zero_pad: bool, scale: bool) -> torch.Tensor:
+    lib = _lib.load()
+    table = _req(table, torch.float32, "table")
+    ids = _req(ids, torch.int64, "ids", table.device)
+    vocab, d = table.shape
+    out = torch.empty(tuple(ids.shape) + (d,), dtype=torch.float32, device=table.device)
+    with torch.cuda.device(table.device):
+        check(lib.edgl_embedding_lookup(table.data_ptr(), vocab, d, int(zero_pad), int(scale), ids.data_ptr(),
+                                        ids.numel(), out.data_ptr(), _stream()))
+    return out
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor) -> torch.Tensor:
+    lib = _lib.load()
+    x = _req(x, torch.float32, "x")
+    if x.dim() != 3:
+        raise ValueError("layernorm expects [B,L,C]")
+    gamma = _req(gamma, torch.float32, "gamma", x.device)
+    beta = _req(beta, torch.float32, "beta", x.device)
+    B, L, Cc = x.shape
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        check(lib.edgl_layernorm(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), B, L, Cc, out.data_ptr(), _stream()))
+    return out
+
+
+def dense(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], act: int = 0) -> torch.Tensor:
+    lib = _lib.load()
+    x = _req(x, torch.float32, "x")
+    w = _req(w, torch.float32, "w", x.device)
+    K, N = w.shape
+    M = x.numel() // K
+    out = torch.empty(tuple(x.shape[:-1]) + (N,), dtype=torch.float32, device=x.device)
+    bb = None if b is None else _req(b, torch.float32, "b", x.device)
+    with torch.cuda.device(x.device):
+        check(lib.edgl_dense(x.data_ptr(), w.data_ptr(), _ptr(bb), M, K, N, act, out.data_ptr(), _stream()))
+    return out
+
+
+def topk(logits: torch.Tensor, k: int, seen_ids: Optional[torch.Tensor] = None):
+    """Sequential.eval ranking on given logits (modified in place when seen_ids is given)."""
+    lib = _lib.load()
+    logits = _req(logits, torch.float32, "logits")
+    B, N = logits.shape
+    seen_len = 0
+    if seen_ids is not None:
+        seen_ids = _req(seen_ids, torch.int64, "seen_ids", logits.device)
+        seen_len = int(seen_ids.shape[1])
+    idx = torch.empty((B, k), dtype=torch.int32, device=logits.device)
+    val = torch.empty((B, k), dtype=torch.float32, device=logits.device)
+    with torch.cuda.device(logits.device):
+        check(lib.edgl_topk(logits.data_ptr(), B, N, _ptr(seen_ids), seen_len, k, idx.data_ptr(), val.data_ptr(),
+                            _stream()))
+    return idx, val
+
+
+def launch_count() -> int:
+    return int(_lib.load().edgl_launch_count())

@@ -1,0 +1,151 @@
+/* easydgl_b200.h - C ABI of libeasydgl_b200.so (sm_100a).
+ *
+ * The reference (cchao0116/EasyDGL) has no FFI / plugin boundary: the boundary for
+ * the hot path is the Python object protocol of its model and layer classes
+ * (SURVEY.md section 8b).  Each entry point below names the reference interface it
+ * replaces (file:line relative to the reference tree).  The Python facade in
+ * easydgl_b200/{model,module}/ keeps the reference's class names and call
+ * signatures and binds these symbols with ctypes (INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *  - every pointer named *_dev / without suffix is a DEVICE pointer unless the
+ *    function name ends in _host; tensors are dense row-major fp32 unless stated;
+ *    ids are int64 (the reference feeds tf.int64 seqs_i, dataloader.py:14-26).
+ *  - every call is asynchronous on the given stream (a cudaStream_t passed as
+ *    void*; NULL = the legacy default stream) except the *_host calls, which
+ *    synchronise that stream before returning.
+ *  - return value: 0 = ok, negative = error (EDGL_E*); edgl_last_error() returns a
+ *    thread-local message.  No call allocates device memory except edgl_create,
+ *    edgl_commit and edgl_reserve.
+ *  - weights are BORROWED: the caller keeps the device buffers alive for the life
+ *    of the handle (or until the next edgl_set_tensor for that name).
+ */
+#ifndef EASYDGL_B200_H
+#define EASYDGL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EDGL_OK 0
+#define EDGL_EINVAL (-1)   /* bad argument / shape / alignment */
+#define EDGL_ESTATE (-2)   /* call order (e.g. forward before commit, missing tensor) */
+#define EDGL_ECUDA (-3)    /* CUDA runtime error (message holds cudaGetErrorString) */
+#define EDGL_ENOMEM (-4)   /* workspace allocation failed */
+#define EDGL_EARCH (-5)    /* device is not sm_100 */
+
+#define EDGL_MODEL_EASYDGL 0 /* src/model/EasyDGL.py */
+#define EDGL_MODEL_CTSMA 1   /* src/model/CTSMA.py */
+
+typedef struct edgl_handle edgl_handle;
+
+/* Mirrors what Model(num_items, FLAGS) derives in its ctor
+ * (EasyDGL.py:37-67, CTSMA.py:22-44, Base.py:92-104). */
+typedef struct edgl_config {
+  int32_t model;       /* EDGL_MODEL_* */
+  int32_t max_batch;   /* workspace is sized for this many sequences per call */
+  int32_t seq_len;     /* L: length of seqs_i (EasyDGL: FLAGS.seqslen+1, EasyDGL.py:40; CTSMA: FLAGS.seqslen) */
+  int32_t num_units;   /* d  (FLAGS.num_units) */
+  int32_t num_heads;   /* h  (FLAGS.num_heads) */
+  int32_t num_blocks;  /* FLAGS.num_blocks */
+  int32_t num_events;  /* E = mark_lookup_table.shape[-1] (EasyDGL.py:46) */
+  int32_t num_rows;    /* rows of the item table = logit columns (EasyDGL: num_items+1, EasyDGL.py:41) */
+  int32_t mark_rows;   /* rows of mark_lookup_table */
+  int32_t topk;        /* K of tf.nn.top_k (Base.py:181 hard-codes 100) */
+  float time_scale;    /* FLAGS.time_scale (EasyDGL.py:43) */
+  int64_t mask_id;     /* [MASK] token id = FLAGS.num_items for EasyDGL (EasyDGL.py:39); -1 for CTSMA */
+  int32_t shard_rank;  /* this handle owns logit columns [rank*ceil(N1/world), ...) - SURVEY 8e */
+  int32_t shard_world; /* 1 = unsharded */
+} edgl_config;
+
+const char* edgl_last_error(void);
+int edgl_version(void);
+/* Number of CUDA kernels this library has launched in this process (bench.py's gpu_launches). */
+int64_t edgl_launch_count(void);
+
+/* Model(num_items, FLAGS) - EasyDGL.py:37 / CTSMA.py:22.  Uses the current CUDA device. */
+int edgl_create(const edgl_config* cfg, edgl_handle** out);
+int edgl_destroy(edgl_handle* h);
+int edgl_get_config(const edgl_handle* h, edgl_config* out);
+
+/* Bind one variable of the reference graph (tf.get_variable / tf.layers.dense kernels)
+ * by name; block = -1 for model-level tensors.  numel is checked against the config.
+ * Names:
+ *   model level : item_embs [N1,d]  pos_embs [L,d]  output_bias [N1-1]  mark_table int64 [mark_rows,E]
+ *     EasyDGL   : mark_embs [E,d]  tr_w [d,d] tr_b tr_ln_g tr_ln_b [d]
+ *     CTSMA     : out_ln_g out_ln_b [d]
+ *   per block   : int_w [dh+1,dh*E] int_b [dh*E] int_weight [E,dh] int_scaling [E]
+ *     EasyDGL   : qkvt_w [Cin,4d] qkvt_b [4d]  ao_w [d,d] ao_b ao_ln_g ao_ln_b
+ *                 ff1_w [d,2d] ff1_b  ff2_w [2d,d] ff2_b  ff_ln_g ff_ln_b      (Cin = 3d for block 0 else d)
+ *     CTSMA     : ln1_g ln1_b [Cin]  {q,k,v,t}_w [Cin,d] {q,k,v,t}_b [d]  ln2_g ln2_b [d]
+ *                 ff1_w [d,d] ff1_b ff2_w [d,d] ff2_b                          (Cin = 2d for block 0 else d)
+ * All fp32 except mark_table (int64, values in [0,E): they index mark_embs, EasyDGL.py:87). */
+int edgl_set_tensor(edgl_handle* h, const char* name, int block, const void* dev_ptr, int64_t numel);
+/* Derive the device-side constants that depend only on weights (packed K|V|T kernels,
+ * position/mark contributions of the block-0 QKVT dense, uint8 mark table).  Call after
+ * the last edgl_set_tensor and again whenever a bound tensor's contents change. */
+int edgl_commit(edgl_handle* h, void* stream);
+
+/* model(features, is_training=False) -> logits [B, N1]        (EasyDGL.py:69-151 / CTSMA.py:46-91)
+ * seqs_i int64 [B,L]; seqs_t fp32 [B,L] (CTSMA: [B,L+1], dataloader.py:99). */
+int edgl_forward_logits(edgl_handle* h, const int64_t* seqs_i, const float* seqs_t, int B, float* logits,
+                        void* stream);
+/* model.eval(features, labels, mask_seen) ranking part (Base.py:150-181): forward, optional
+ * -inf at every id in seqs_i, top-K with ties -> lower index.  idx int32 [B,K], val fp32 [B,K]
+ * (the masked logits; ranking on them equals ranking on softmax).  Unsharded handles only. */
+int edgl_forward_topk(edgl_handle* h, const int64_t* seqs_i, const float* seqs_t, int B, int mask_seen,
+                      int32_t* idx, float* val, void* stream);
+/* Same call with HOST buffers (pinned or pageable): H2D of seqs_i/seqs_t, forward, D2H of idx/val,
+ * stream synchronised on return.  This is the end-to-end call bench.py times as "e2e". */
+int edgl_forward_topk_host(edgl_handle* h, const int64_t* seqs_i_host, const float* seqs_t_host, int B,
+                           int mask_seen, int32_t* idx_host, float* val_host, void* stream);
+
+/* ---- the two halves of the forward, for the column-sharded multi-GPU path ---- */
+/* Encoder up to y = hidden[:, -1]  [B,d]  (EasyDGL.py:69-146 / CTSMA.py:46-87). */
+int edgl_encode(edgl_handle* h, const int64_t* seqs_i, const float* seqs_t, int B, float* y, void* stream);
+/* y [Bt,d] x this handle's item-table shard -> logits + bias (EasyDGL.py:149-150), optional seen-mask
+ * with seen_ids int64 [Bt,seen_len] (may be NULL), local top-K with GLOBAL column ids. */
+int edgl_logits_topk(edgl_handle* h, const float* y, const int64_t* seen_ids, int seen_len, int Bt,
+                     int32_t* cand_idx, float* cand_val, void* stream);
+/* K-way merge of G per-shard candidate lists [G,Bt,K] -> [Bt,K]; ties -> lower global index (Base.py:181). */
+int edgl_topk_merge(const float* cand_val, const int32_t* cand_idx, int G, int Bt, int K, int32_t* idx,
+                    float* val, void* stream);
+
+/* ---- layer-level entry points (one per reference layer, for unit parity) ---- */
+/* C.TimeSinusoidCoding(d).code(ts)  (coding.py:132-149): ts fp32 [B,L] already scaled -> [B,L,d]. */
+int edgl_time_sinusoid_code(const float* ts, int B, int L, int d, float* out, void* stream);
+/* C.Embedding(vocab,d,zero_pad,scale)(ids)  (coding.py:45-64): table [vocab,d] raw variable. */
+int edgl_embedding_lookup(const float* table, int vocab, int d, int zero_pad, int scale, const int64_t* ids,
+                          int64_t n_ids, float* out, void* stream);
+/* EasyDGL.__call__ input assembly (EasyDGL.py:70-95) / CTSMA (CTSMA.py:47-60):
+ * X0 [B,L,3d] (CTSMA [B,L,2d]); spans fp32 [B,L]; marks uint8 [B,L,E]. Any output may be NULL. */
+int edgl_embed(edgl_handle* h, const int64_t* seqs_i, const float* seqs_t, int B, float* X0, float* spans,
+               uint8_t* marks, void* stream);
+/* T.BiMAU(...)(queries, keys, masks, intervals, marks, is_training=False)  (temporal.py:404-452)
+ * and T.MAU(...)(..., causality)  (temporal.py:335-390), using block `block`'s weights.
+ * queries [B,L,Cq]; keys [B,L,Ck] (ignored for EasyDGL handles, Q15); kmask uint8 [B,L] (1 = real key);
+ * intervals [B,L]; marks uint8 [B,L,E].  Outputs: out [B,L,d]; lam [h*B,L,E] head-major (may be NULL). */
+int edgl_attention_layer(edgl_handle* h, int block, const float* queries, int Cq, const float* keys, int Ck,
+                         const uint8_t* kmask, const float* intervals, const uint8_t* marks, int B,
+                         int causality, float* out, float* lam, void* stream);
+/* T.MAU.intensity(H, intervals, mark_onehot)  (temporal.py:281-315) with block `block`'s weights:
+ * H [h*B,L,dh] head-major -> G [h*B,L,L] (no set_diag), lam [h*B,L,E]. */
+int edgl_intensity(edgl_handle* h, int block, const float* H, const float* intervals, const uint8_t* marks,
+                   int B, float* G, float* lam, void* stream);
+/* Base.layernorm(x)  (Base.py:12-67): joint (L,C) statistics per sample. x [B,L,C] -> out [B,L,C]. */
+int edgl_layernorm(const float* x, const float* gamma, const float* beta, int B, int L, int C, float* out,
+                   void* stream);
+/* tf.layers.dense(x, N, activation) (act: 0 none, 1 gelu-erf EasyDGL.py:19-32, 2 relu): x [M,K] @ w [K,N] + b. */
+int edgl_dense(const float* x, const float* w, const float* b, int M, int K, int N, int act, float* out,
+               void* stream);
+/* Sequential.eval ranking on given logits (Base.py:156-181): logits [B,N] are modified in place
+ * (seen ids -> -inf) when seen_ids != NULL. */
+int edgl_topk(float* logits, int B, int N, const int64_t* seen_ids, int seen_len, int K, int32_t* idx,
+              float* val, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EASYDGL_B200_H */

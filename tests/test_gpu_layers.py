@@ -1,0 +1,208 @@
+"""GPU parity of every layer-level C-ABI entry point against the CPU oracle.
+
+Each test reads like a test the reference could have had for the layer it names
+(the reference has none).  Tolerance: 1e-3 relative (north star),
+stated per assertion; integer outputs bit-exact.
+"""
+import math
+
+import pytest
+import torch
+
+from helpers import O, assert_close, case, synth
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _engine(cfg, W, max_batch, **kw):
+    from easydgl_b200.engine import Engine
+    return Engine(cfg, W, max_batch=max_batch, device=DEV, **kw)
+
+
+def test_library_loads_and_reports_version():
+    from easydgl_b200 import _lib
+    lib = _lib.load()
+    assert lib.edgl_version() >= 100
+
+
+@pytest.mark.parametrize("d", [8, 50, 64, 128])
+def test_time_sinusoid_code(d):
+    """C.TimeSinusoidCoding.code (coding.py:137-149) on Netflix-scale scaled timestamps."""
+    from easydgl_b200 import engine
+    g = torch.Generator().manual_seed(1)
+    ts = (torch.rand(7, 33, generator=g) * 2000 + 10800).float()  # days since epoch / 1
+    ts[0, :5] = 0.0  # padded slots (Q10)
+    out = engine.time_sinusoid_code(ts.to(DEV), d).cpu()
+    ref32 = O.time_sinusoid_code(ts, d, torch.float32)
+    ref64 = O.time_sinusoid_code(ts, d, torch.float64)
+    assert_close(out, ref64, 1e-5, "time code vs fp64")
+    assert_close(out, ref32, 1e-5, "time code vs fp32")
+    assert torch.equal(out[0, 0, 0::2], torch.zeros(d // 2)) and torch.equal(out[0, 0, 1::2], torch.ones(d // 2))
+
+
+def test_time_sinusoid_code_rank_assert():
+    from easydgl_b200 import engine
+    with pytest.raises(AssertionError):
+        engine.time_sinusoid_code(torch.zeros(3, 4, 5, device=DEV), 8)
+
+
+@pytest.mark.parametrize("zero_pad,scale", [(True, True), (True, False), (False, False)])
+def test_embedding_lookup(zero_pad, scale):
+    """C.Embedding.__call__ (coding.py:45-64): bit-exact gather (x sqrt(d) is one fp32 multiply)."""
+    from easydgl_b200 import engine
+    g = torch.Generator().manual_seed(2)
+    table = torch.randn(97, 24, generator=g)
+    ids = torch.randint(0, 97, (5, 11), generator=g)
+    ids[0, 0] = 0
+    out = engine.embedding_lookup(table.to(DEV), ids.to(DEV), zero_pad, scale).cpu()
+    tab = O.zero_pad_table(table) if zero_pad else table
+    ref = O.embedding(tab, ids, scale, 24)
+    assert torch.equal(out, ref)
+
+
+@pytest.mark.parametrize("name", ["easy_a", "easy_b", "easy_c", "ctsma_a", "ctsma_b"])
+def test_embed_input_assembly(name):
+    """EasyDGL.py:70-95 / CTSMA.py:47-60: X0, spans, marks."""
+    cfg, inp, W = case(name, batch=9)
+    eng = _engine(cfg, W, 9)
+    X0, spans, marks = eng.embed(inp["seqs_i"].to(DEV), inp["seqs_t"].to(DEV))
+    fn = O.easydgl_inputs if cfg.model == "EasyDGL" else O.ctsma_inputs
+    rX, rk, rs, rm = fn(inp["seqs_i"], inp["seqs_t"], O._cast(W, torch.float64), cfg, torch.float64)
+    assert torch.equal(marks.cpu().long(), rm), "marks must be bit-exact"
+    assert_close(spans.cpu(), rs, 1e-6, "spans")
+    assert_close(X0.cpu(), rX, 1e-5, "X0")
+
+
+@pytest.mark.parametrize("B,L,C", [(3, 7, 8), (5, 31, 64), (2, 100, 128), (2, 300, 256)])
+def test_layernorm_joint_axes(B, L, C):
+    """Base.layernorm (Base.py:12-67): statistics over (L,C) jointly (Q2)."""
+    from easydgl_b200 import engine
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(B, L, C, generator=g) * 2.0 + 0.7
+    gam = torch.randn(C, generator=g) * 0.2 + 1.0
+    bet = torch.randn(C, generator=g) * 0.3
+    out = engine.layernorm(x.to(DEV), gam.to(DEV), bet.to(DEV)).cpu()
+    ref = O.layernorm(x.double(), gam.double(), bet.double())
+    assert_close(out, ref, 1e-5, "layernorm")
+    # it is NOT the per-position layernorm
+    per_pos = torch.nn.functional.layer_norm(x, (C,), gam, bet, 1e-12)
+    assert (out - per_pos).abs().max() > 1e-3
+
+
+@pytest.mark.parametrize("M,K,N,act", [(5, 17, 9, 0), (130, 64, 128, 1), (257, 144, 512, 0), (64, 130, 66, 2),
+                                       (1000, 384, 512, 1)])
+def test_dense(M, K, N, act):
+    """tf.layers.dense with none / gelu-erf (EasyDGL.py:19-32) / relu."""
+    from easydgl_b200 import engine
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(M, K, generator=g)
+    w = torch.randn(K, N, generator=g) / math.sqrt(K)
+    b = torch.randn(N, generator=g)
+    out = engine.dense(x.to(DEV), w.to(DEV), b.to(DEV), act).cpu()
+    ref = x.double() @ w.double() + b.double()
+    if act == 1:
+        ref = O.gelu(ref)
+    elif act == 2:
+        ref = torch.relu(ref)
+    assert_close(out, ref, 1e-5, "dense act=%d" % act)
+
+
+@pytest.mark.parametrize("name", ["easy_a", "easy_b", "easy_c", "ctsma_b"])
+def test_intensity(name):
+    """T.MAU.intensity (temporal.py:281-315): G [hB,L,L] and lam [hB,L,E], literal 4-D form as reference."""
+    cfg, inp, W = case(name, batch=5)
+    eng = _engine(cfg, W, 5)
+    h, dh, E, L = cfg.num_heads, cfg.num_units // cfg.num_heads, cfg.num_events, cfg.L
+    g = torch.Generator().manual_seed(5)
+    H = torch.randn(h * 5, L, dh, generator=g)
+    iv = torch.rand(5, L, generator=g) * 30
+    fn = O.easydgl_inputs if cfg.model == "EasyDGL" else O.ctsma_inputs
+    _, _, _, marks = fn(inp["seqs_i"], inp["seqs_t"], O._cast(W, torch.float64), cfg, torch.float64)
+    blk = O._cast(W["blocks"][0], torch.float64)
+    rG, rl = O.intensity(H.double(), iv.double(), marks, blk, h, E, literal=True)
+    G, lam = eng.intensity(0, H.to(DEV), iv.to(DEV), marks.to(torch.uint8).to(DEV))
+    assert_close(lam.cpu(), rl, 1e-4, "lam")
+    assert_close(G.cpu(), rG, 1e-4, "G")
+
+
+@pytest.mark.parametrize("name", ["easy_a", "easy_b", "easy_c"])
+def test_bimau_layer(name):
+    """T.BiMAU.__call__ (temporal.py:404-452) incl. all-padding rows (Q8) and set_diag (Q4)."""
+    cfg, inp, W = case(name, batch=6)
+    eng = _engine(cfg, W, 6)
+    W64 = O._cast(W, torch.float64)
+    X0, kmask, spans, marks = O.easydgl_inputs(inp["seqs_i"], inp["seqs_t"], W64, cfg, torch.float64)
+    blk = W64["blocks"][0]
+    rO, rl = O.bimau(X0, kmask, spans, marks, blk, cfg.num_units, cfg.num_heads, cfg.num_events, literal=True)
+    out, lam = eng.attention_layer(0, X0.float().to(DEV), None, kmask.to(torch.uint8).to(DEV),
+                                   spans.float().to(DEV), marks.to(torch.uint8).to(DEV))
+    assert_close(lam.cpu(), rl, 1e-4, "BiMAU lam")
+    assert_close(out.cpu(), rO, 1e-4, "BiMAU out")
+
+
+@pytest.mark.parametrize("name,causal", [("ctsma_a", True), ("ctsma_b", True), ("ctsma_b", False)])
+def test_mau_layer(name, causal):
+    """T.MAU.__call__ (temporal.py:335-390): separate Q (from LN'd queries) and K/V/T (raw keys), causal mask."""
+    cfg, inp, W = case(name, batch=6)
+    eng = _engine(cfg, W, 6)
+    W64 = O._cast(W, torch.float64)
+    X, kmask, spans, marks = O.ctsma_inputs(inp["seqs_i"], inp["seqs_t"], W64, cfg, torch.float64)
+    blk = W64["blocks"][0]
+    qin = O.layernorm(X, blk["ln1_g"], blk["ln1_b"])
+    rO, rl = O.mau(qin, X, kmask, spans, marks, blk, cfg.num_units, cfg.num_heads, cfg.num_events, causal, literal=True)
+    out, lam = eng.attention_layer(0, qin.float().to(DEV), X.float().to(DEV), kmask.to(torch.uint8).to(DEV),
+                                   spans.float().to(DEV), marks.to(torch.uint8).to(DEV), causality=causal)
+    assert_close(lam.cpu(), rl, 1e-4, "MAU lam")
+    assert_close(out.cpu(), rO, 1e-4, "MAU out")
+    if causal:
+        # causal + all-padded history -> uniform attention over ALL keys (the -2^32+1 fill is finite, Q8)
+        assert torch.isfinite(out).all()
+
+
+def test_topk_ties_and_masking():
+    """tf.nn.top_k (Base.py:181): sorted, ties -> lower index; seen ids -> -inf (Base.py:156-163)."""
+    from easydgl_b200 import engine
+    g = torch.Generator().manual_seed(6)
+    B, N, K = 9, 1000, 100
+    logits = torch.randn(B, N, generator=g)
+    logits[0] = 0.5                       # all tied -> indices 0..K-1
+    logits[1, :] = torch.round(logits[1] * 2) / 2  # heavy ties
+    logits[2, 10:400] = float("-inf")     # many masked
+    logits[3, :] = float("-inf")          # everything masked -> ties at -inf, lowest indices
+    logits[4, 5] = float("inf")
+    seen = torch.randint(0, N, (B, 17), generator=g)
+    ref_v, ref_i = O.eval_topk(logits.double(), seen, True, K, rank_on="logits")
+    lg = logits.clone().to(DEV)
+    idx, val = engine.topk(lg, K, seen.to(DEV))
+    assert torch.equal(idx.cpu().long(), ref_i), "top-K indices must be bit-identical"
+    assert torch.equal(val.cpu().double(), ref_v)
+    # in-place masking happened
+    assert torch.isinf(lg.cpu()[5, seen[5]]).all()
+
+
+def test_topk_small_n_pads():
+    from easydgl_b200 import engine
+    logits = torch.tensor([[0.1, 0.7, -0.2]], device=DEV)
+    idx, val = engine.topk(logits, 5)
+    assert idx.cpu().tolist() == [[1, 0, 2, -1, -1]]
+
+
+@pytest.mark.parametrize("G", [2, 3, 8])
+def test_topk_merge_equals_global(G):
+    """merging per-shard top-K must equal the single-device top-K bit for bit."""
+    from easydgl_b200 import engine
+    g = torch.Generator().manual_seed(7)
+    B, N, K = 11, 4001, 100
+    logits = torch.round(torch.randn(B, N, generator=g) * 8) / 8  # ties across shards
+    gi, gv = engine.topk(logits.clone().to(DEV), K)
+    per = (N + G - 1) // G
+    ci, cv = [], []
+    for r in range(G):
+        c0, c1 = r * per, min(N, (r + 1) * per)
+        i, v = engine.topk(logits[:, c0:c1].contiguous().to(DEV), K)
+        i = torch.where(i >= 0, i + c0, i)
+        ci.append(i)
+        cv.append(v)
+    mi, mv = engine.topk_merge(torch.stack(cv), torch.stack(ci))
+    assert torch.equal(mi, gi) and torch.equal(mv, gv)

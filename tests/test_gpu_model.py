@@ -1,0 +1,175 @@
+"""GPU parity of the whole forward path (model(features, False) and model.eval ranking)
+against the CPU oracle, through the C ABI.  Tolerance 1e-3 relative on logits (north
+star); top-K index sets identical up to near-ties at the cut (tie-aware)."""
+import json
+import os
+
+import pytest
+import torch
+
+from helpers import O, assert_close, case, synth
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+
+
+def _engine(cfg, W, max_batch, **kw):
+    from easydgl_b200.engine import Engine
+    return Engine(cfg, W, max_batch=max_batch, device=DEV, **kw)
+
+
+def _log(name, rec):
+    os.makedirs(OUT, exist_ok=True)
+    with open(os.path.join(OUT, "parity.jsonl"), "a") as fh:
+        fh.write(json.dumps(dict(test=name, **rec)) + "\n")
+
+
+def _check_model(name, batch, mode="parity", k=100, **over):
+    cfg, inp, W = case(name, batch=batch, mode=mode, **over)
+    k = min(k, cfg.num_rows)
+    eng = _engine(cfg, W, batch, topk=k)
+    ids, ts = inp["seqs_i"], inp["seqs_t"]
+    logits = eng.forward_logits(ids.to(DEV), ts.to(DEV)).cpu()
+    ref64 = O.forward(ids, ts, W, cfg, dtype=torch.float64)
+    ref32 = O.forward(ids, ts, W, cfg, dtype=torch.float32)
+    assert torch.equal(logits[:, 0], torch.full((batch,), -1000.0)), "column 0 must be exactly -1000 (Q11)"
+    e64 = assert_close(logits[:, 1:], ref64[:, 1:], 1e-3, name + " logits vs fp64 oracle")
+    e32 = assert_close(logits[:, 1:], ref32[:, 1:], 1e-3, name + " logits vs fp32 oracle")
+    # ranking
+    idx, val = eng.forward_topk(ids.to(DEV), ts.to(DEV), mask_seen=True)
+    idx, val = idx.cpu().long(), val.cpu()
+    masked64 = O.mask_seen_logits(ref64, ids)
+    abs_err = float((logits.double() - ref64).abs().max())
+    res = O.topk_set_compare(idx, masked64, k, tau=4 * abs_err)
+    # the returned values are the masked logits of the returned indices, sorted, ties by index
+    mine = O.mask_seen_logits(logits, ids)
+    assert torch.equal(val, torch.gather(mine, 1, idx)), "top-K values must be the kernel's own masked logits"
+    ri_v, ri_i = O.eval_topk(logits, ids, True, k, rank_on="logits")
+    assert torch.equal(idx, ri_i), "top-K must be the exact ranking of the kernel's own logits"
+    assert res["bad"] == 0, res
+    # literal reference ranking (softmax then top_k, Base.py:164,181) agrees with ranking logits in fp64
+    _, lit = O.eval_topk(ref64, ids, True, k, rank_on="probs")
+    _, lg = O.eval_topk(ref64, ids, True, k, rank_on="logits")
+    finite = torch.isfinite(torch.gather(masked64, 1, lg)).all(dim=1)
+    _log(name, dict(batch=batch, rel_err_fp64=e64, rel_err_fp32=e32, abs_err=abs_err, topk=res,
+                    probs_vs_logits_rank_equal=bool(torch.equal(lit[finite], lg[finite]))))
+    return eng, cfg, inp, W, logits, idx, val
+
+
+@pytest.mark.parametrize("name", ["easy_a", "easy_b", "easy_c", "ctsma_a", "ctsma_b"])
+def test_forward_small_parity_weights(name):
+    _check_model(name, batch=8)
+
+
+@pytest.mark.parametrize("name", ["easy_b", "ctsma_b"])
+def test_forward_reference_initialisers(name):
+    """Weights drawn with the reference's own initialisers (glorot / N(0,0.02) / zeros / ones)."""
+    _check_model(name, batch=8, mode="reference")
+
+
+def test_forward_reference_default_length():
+    """The reference default --seqslen=30 (main.py:38) -> L=31, a non-multiple-of-8 length."""
+    _check_model("easy_b", batch=5, seqslen=30)
+
+
+def test_forward_onehot_marks():
+    _check_model("easy_a", batch=6, onehot=True)
+
+
+def test_forward_c1_config():
+    """BASELINE.json configs[0]: EasyDGL d=64 L=100 18K items B=32 h=8 (the reference's CPU case)."""
+    _check_model("C1", batch=32)
+
+
+def test_forward_c3_shape_small_batch():
+    """BASELINE.json configs[2] shape (CTSMA d=64 L=100 h=4 blocks=2) at a small batch."""
+    _check_model("C3", batch=16)
+
+
+def test_forward_c2_shape_small_batch():
+    """BASELINE.json configs[1] shape (EasyDGL d=128 L=100 h=8) at a small batch."""
+    _check_model("C2", batch=16)
+
+
+def test_batch_invariance_and_determinism():
+    """Sequences are independent (every op incl. LayerNorm is per sample): a row's logits must not
+    depend on its batch-mates, and two runs must agree bit for bit."""
+    cfg, inp, W = case("easy_b", batch=12)
+    eng = _engine(cfg, W, 12)
+    ids, ts = inp["seqs_i"].to(DEV), inp["seqs_t"].to(DEV)
+    a = eng.forward_logits(ids, ts)
+    b = eng.forward_logits(ids, ts)
+    assert torch.equal(a, b)
+    c = eng.forward_logits(ids[3:7].contiguous(), ts[3:7].contiguous())
+    assert torch.equal(a[3:7], c)
+
+
+@pytest.mark.parametrize("G", [2, 4, 8])
+def test_sharded_topk_equals_single(G):
+    """Column-sharded logits + per-shard top-K + merge == single-device top-K, bit for bit."""
+    from easydgl_b200 import engine
+    cfg, inp, W = case("easy_b", batch=10)
+    ids, ts = inp["seqs_i"].to(DEV), inp["seqs_t"].to(DEV)
+    single = _engine(cfg, W, 10)
+    gi, gv = single.forward_topk(ids, ts, True)
+    y = single.encode(ids, ts)
+    ci, cv = [], []
+    for r in range(G):
+        sh = _engine(cfg, W, 10, shard_rank=r, shard_world=G)
+        i, v = sh.logits_topk(y, ids)
+        ci.append(i)
+        cv.append(v)
+    mi, mv = engine.topk_merge(torch.stack(cv), torch.stack(ci))
+    assert torch.equal(mi, gi) and torch.equal(mv, gv)
+
+
+def test_host_entry_point_matches_device_entry_point():
+    cfg, inp, W = case("easy_a", batch=7)
+    eng = _engine(cfg, W, 7)
+    ids, ts = inp["seqs_i"], inp["seqs_t"]
+    gi, gv = eng.forward_topk(ids.to(DEV), ts.to(DEV), True)
+    K = eng.K
+    hi = torch.empty((7, K), dtype=torch.int32).pin_memory()
+    hv = torch.empty((7, K), dtype=torch.float32).pin_memory()
+    eng.forward_topk_host(ids.pin_memory(), ts.pin_memory(), hi, hv, True)
+    assert torch.equal(hi, gi.cpu()) and torch.equal(hv, gv.cpu())
+
+
+def test_error_conventions():
+    """shape / state errors surface as exceptions, not silent garbage."""
+    from easydgl_b200._lib import EdglError
+    cfg, inp, W = case("easy_a", batch=4)
+    eng = _engine(cfg, W, 4)
+    ids, ts = inp["seqs_i"].to(DEV), inp["seqs_t"].to(DEV)
+    with pytest.raises(ValueError):
+        eng.forward_logits(ids[:, :-1].contiguous(), ts)
+    with pytest.raises(ValueError):
+        eng.forward_logits(torch.cat([ids, ids, ids]), torch.cat([ts, ts, ts]))  # > max_batch
+    with pytest.raises(AssertionError):
+        eng.forward_logits(ids, ts.reshape(-1))
+    W2 = dict(W)
+    W2["mark_table"] = W["mark_table"] + cfg.num_events  # values no longer index mark_embs
+    with pytest.raises(ValueError):
+        _engine(cfg, W2, 4)
+    W3 = {k: v for k, v in W.items() if k != "tr_w"}
+    with pytest.raises(EdglError):
+        _engine(cfg, W3, 4)
+
+
+def test_golden_fixtures():
+    """Committed fixtures (tests/golden/, made by tests/golden/make_golden.py from the fp64 oracle)."""
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    files = sorted(f for f in os.listdir(gdir) if f.endswith(".pt"))
+    assert files, "no golden fixtures"
+    for f in files:
+        g = torch.load(os.path.join(gdir, f))
+        cfg = synth.make_config(**g["cfg"])
+        eng = _engine(cfg, g["weights"], g["seqs_i"].shape[0], topk=g["topk_idx"].shape[1])
+        logits = eng.forward_logits(g["seqs_i"].to(DEV), g["seqs_t"].to(DEV)).cpu()
+        assert_close(logits[:, 1:], g["logits64"][:, 1:], 1e-3, f)
+        idx, _ = eng.forward_topk(g["seqs_i"].to(DEV), g["seqs_t"].to(DEV), True)
+        masked = O.mask_seen_logits(g["logits64"], g["seqs_i"])
+        err = float((logits.double() - g["logits64"]).abs().max())
+        res = O.topk_set_compare(idx.cpu().long(), masked, idx.shape[1], tau=4 * err)
+        assert res["bad"] == 0, (f, res)

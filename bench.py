@@ -1,0 +1,366 @@
+#!/usr/bin/env python
+"""bench.py - sequences/sec of the EasyDGL eval forward (+ seen-mask + top-100).
+
+    python bench.py --gpus 1 --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle port)
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path over one batch of B=4096 synthetic Netflix-schema
+sequences (BASELINE.json configs[1], "C2").  At N>1 every rank gets its own B sequences (weak
+scaling) and the item table / logits are column-sharded (easydgl_b200/sharded.py).
+
+One JSON line on stdout (rank 0).  `value` = device-resident inputs, CUDA-event timed, max over
+ranks; `e2e` = the same work through edgl_forward_topk_host with pinned HOST buffers (H2D + D2H
+inside the timed region); `roofline` = the dominant kernel's algorithmic TFLOP/s from CUDA events
+recorded on the launch stream inside the timed region; `cpu_baseline` = the fp32 CPU oracle (the
+reference cannot run here: TensorFlow 2.3.4 is not installable) on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+from easydgl_b200 import synth  # noqa: E402
+
+WORKLOAD = "C2"
+NUM_INPUT_SETS = 4  # rotating distinct input batches
+
+
+def workload_desc(cfg, B, n_gpus):
+    return {
+        "workload": "%s: %s d=%d L=%d items=%d B=%d/GPU h=%d blocks=%d E=%d; eval forward + mask_seen + top-%d"
+                    % (WORKLOAD, cfg.model, cfg.num_units, cfg.L, cfg.num_items, B, cfg.num_heads, cfg.num_blocks,
+                       cfg.num_events, cfg.topk),
+        "global_batch": B * n_gpus,
+        "parallelism": "single GPU" if n_gpus == 1 else
+        "batch-sharded encoder + column-sharded item table (%d shards), 2 NCCL all-gathers" % n_gpus,
+        "l2": "per-step working set ~3 GB of activations >> 126 MB L2; %d rotating input batches" % NUM_INPUT_SETS,
+        "weights": "reference initialisers (glorot / N(0,0.02)), seed 9876",
+    }
+
+
+# ----------------------------------------------------------------------------- FLOP model
+def stage_flops(cfg, B):
+    """Algorithmic FLOPs (2*MAC) each stage's kernel performs per launch on B sequences."""
+    L, d, h, E, N1 = cfg.L, cfg.num_units, cfg.num_heads, cfg.num_events, cfg.num_rows
+    dh = d // h
+    return {
+        "qkvt_gemm": 2.0 * B * L * (d + E) * 4 * d,                  # folded block-0 QKVT dense
+        "attention": B * (6.0 * L * L * d + 2.0 * L * d * E * (dh + 2) + 2.0 * h * L * L * E),
+        "ao_gemm": 2.0 * B * L * d * d,
+        "ff1_gemm": 4.0 * B * L * d * d,
+        "ff2_gemm": 4.0 * B * L * d * d,
+        "tr_gemm": 2.0 * B * L * d * d,
+        "logits_gemm": 2.0 * B * d * N1,
+    }
+
+
+def stage_bytes(cfg, B):
+    """Compulsory HBM bytes per launch for the memory-bound stages."""
+    L, d, E, N1, K = cfg.L, cfg.num_units, cfg.num_events, cfg.num_rows, cfg.topk
+    rows = B * L
+    return {
+        "embed": rows * (8 + 4 + 4 * d) + rows * 4 * (d + E) + rows * (4 + E + 1),
+        "ln_att": 2.0 * rows * d * 4, "ln_ff": 2.0 * rows * d * 4, "ln_out": rows * d * 4 + B * d * 4,
+        "topk": B * N1 * 4 + B * K * 8,
+    }
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples SM clock / throttle reasons during the timed region (pynvml, 20 ms period)."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {
+            "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+            "hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+            "hw_power_brake": getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80),
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+
+    def start(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join()
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ----------------------------------------------------------------------------- CPU reference arm
+def cpu_reference(cfg, W, n_seqs, steps, warmup, threads):
+    """Times the fp32 CPU oracle (contracted mode, torch-CPU/MKL) on `n_seqs` sequences per step."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import easydgl_oracle as O
+    torch.set_num_threads(threads)
+    inp = synth.make_inputs(cfg, n_seqs, seed=synth.SEED + 100)
+    ids, ts = inp["seqs_i"], inp["seqs_t"]
+    chunk = 128
+
+    def one_step():
+        for s in range(0, n_seqs, chunk):
+            logits = O.forward(ids[s:s + chunk], ts[s:s + chunk], W, cfg, dtype=torch.float32)
+            O.eval_topk(logits, ids[s:s + chunk], True, cfg.topk, rank_on="probs")
+
+    with torch.no_grad():
+        for _ in range(warmup):
+            one_step()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            one_step()
+        dt = time.perf_counter() - t0
+    return n_seqs * steps / dt, dt / steps
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cfg = synth.named_config(WORKLOAD)
+    W = synth.make_weights(cfg, mode="reference")
+    threads = os.cpu_count() or 1
+    n_seqs = 256
+    sps, step_s = cpu_reference(cfg, W, n_seqs, args.steps, max(args.warmup, 1), threads)
+    sample = "%d sequences/step of the %s workload (2 chunks of 128), fp32 torch-CPU oracle, contracted gate" % (
+        n_seqs, WORKLOAD)
+    line = {
+        "impl": "reference", "metric": "sequences/sec", "value": sps, "unit": "seq/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_desc(cfg, synth.CONFIGS[WORKLOAD]["batch"], args.gpus),
+        "cpu_baseline": {"value": sps, "unit": "seq/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": sps, "unit": "seq/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "the reference needs tensorflow-gpu==2.3.4 (not installable here); this arm times oracle/, the "
+                "op-for-op CPU restatement of its forward path, with all host threads",
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ----------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch.distributed as dist
+    from easydgl_b200 import engine as E
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus %d needs torchrun with %d ranks" % (args.gpus, args.gpus))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfg = synth.named_config(WORKLOAD)
+    B = args.batch or synth.CONFIGS[WORKLOAD]["batch"]
+    W = synth.make_weights(cfg, mode="reference")
+    eng = E.Engine(cfg, W, max_batch=B, device=dev, shard_rank=rank if world > 1 else 0,
+                   shard_world=world if world > 1 else 1)
+    ranker = None
+    if world > 1:
+        from easydgl_b200.sharded import ShardedRanker
+        ranker = ShardedRanker(eng)
+
+    sets = []
+    for i in range(NUM_INPUT_SETS):
+        inp = synth.make_inputs(cfg, B, seed=synth.SEED + 1000 * rank + i)
+        sets.append((inp["seqs_i"].pin_memory(), inp["seqs_t"].pin_memory()))
+    dsets = [(a.to(dev), b.to(dev)) for a, b in sets]
+    idx = torch.empty((B, cfg.topk), dtype=torch.int32, device=dev)
+    val = torch.empty((B, cfg.topk), dtype=torch.float32, device=dev)
+
+    def step(i):
+        a, b = dsets[i % NUM_INPUT_SETS]
+        if ranker is None:
+            eng.forward_topk(a, b, True, out=(idx, val))
+        else:
+            ranker.forward_topk(a, b, True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    eng.profile(True)
+    launches0 = E.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.start()
+    barrier()
+    ev0.record()
+    for i in range(args.steps):
+        step(i)
+    ev1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms = ev0.elapsed_time(ev1)
+    launches = E.launch_count() - launches0
+    prof = eng.profile_read()
+    eng.profile(False)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * B * args.steps / (ms * 1e-3)
+
+    # ---- e2e: pinned host inputs -> H2D -> forward -> top-K -> D2H, every step
+    h_idx = torch.empty((B, cfg.topk), dtype=torch.int32).pin_memory()
+    h_val = torch.empty((B, cfg.topk), dtype=torch.float32).pin_memory()
+
+    def step_e2e(i):
+        a, b = sets[i % NUM_INPUT_SETS]
+        if ranker is None:
+            eng.forward_topk_host(a, b, h_idx, h_val, True)
+        else:
+            da, db = a.to(dev, non_blocking=True), b.to(dev, non_blocking=True)
+            ri, rv = ranker.forward_topk(da, db, True)
+            h_idx.copy_(ri, non_blocking=True)
+            h_val.copy_(rv, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+    for i in range(min(args.warmup, 3)):
+        step_e2e(i)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for i in range(args.steps):
+        step_e2e(i)
+    e1.record()
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    e2e_ms = max(e0.elapsed_time(e1), wall_ms)  # host-synchronous calls: wall clock bounds the device span
+    if world > 1:
+        t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_value = world * B * args.steps / (e2e_ms * 1e-3)
+    h2d = B * cfg.L * 8 + B * cfg.ts_len * 4
+    d2h = B * cfg.topk * 8
+
+    line = None
+    if rank == 0:
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+                peaks = json.load(fh)
+        except Exception:
+            pass
+        tf_peak = peaks.get("bf16_tflops_sustained", 1400.0)
+        peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback (B200_PROFILING.md)"
+        fl, by = stage_flops(cfg, B), stage_bytes(cfg, B)
+        stages = {}
+        total_stage_ms = sum(v[0] for v in prof.values()) or 1.0
+        for name, (sms, cnt) in prof.items():
+            avg = sms / cnt
+            rec = {"ms": round(avg, 4), "launches_per_step": cnt / args.steps, "share": round(sms / total_stage_ms, 4)}
+            scale = 1.0
+            if ranker is not None and name in ("logits_gemm", "topk"):
+                scale = 1.0  # per rank: G*B rows x N1/G columns = same FLOPs/bytes as unsharded
+            if name in fl:
+                rec["tflops"] = round(fl[name] * scale / (avg * 1e-3) / 1e12, 3)
+            if name in by:
+                rec["gbs"] = round(by[name] * scale / (avg * 1e-3) / 1e9, 1)
+            stages[name] = rec
+        dom = max(prof.items(), key=lambda kv: kv[1][0])[0] if prof else None
+        roof = None
+        if dom in fl:
+            ach = fl[dom] / ((prof[dom][0] / prof[dom][1]) * 1e-3) / 1e12
+            roof = {"kernel": dom, "bound": "tensor", "achieved": round(ach, 3), "peak": tf_peak, "unit": "TFLOP/s",
+                    "frac": round(ach / tf_peak, 5), "traffic": None, "peak_source": peak_src,
+                    "note": "algorithmic fp32 FLOPs of the kernel / CUDA-event time; peak is dense bf16 (fp32-exact "
+                            "arithmetic is required by the top-K parity bar, see DESIGN.md)"}
+        elif dom in by:
+            hb = peaks.get("hbm_gbs", 6650.0)
+            ach = by[dom] / ((prof[dom][0] / prof[dom][1]) * 1e-3) / 1e9
+            roof = {"kernel": dom, "bound": "hbm", "achieved": round(ach, 1), "peak": hb, "unit": "GB/s",
+                    "frac": round(ach / hb, 4), "traffic": None, "peak_source": peak_src}
+        line = {
+            "metric": "sequences/sec", "value": value, "unit": "seq/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_desc(cfg, B, world),
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "seq/s", "ms_per_step": e2e_ms / args.steps,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches),
+            "roofline": roof, "stages": stages,
+        }
+        if world == 1 and not args.no_cpu:
+            threads = os.cpu_count() or 1
+            n_seqs = 256
+            sps, step_s = cpu_reference(cfg, W, n_seqs, args.cpu_steps, 1, threads)
+            line["cpu_baseline"] = {
+                "value": sps, "unit": "seq/s", "cores": threads, "kind": "port",
+                "sample": "%d steps x %d sequences of the %s workload (%.1f s), fp32 torch-CPU oracle, contracted gate"
+                          % (args.cpu_steps, n_seqs, WORKLOAD, step_s * args.cpu_steps)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=0, help="override per-GPU batch (debug only)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cpu-steps", type=int, default=20)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

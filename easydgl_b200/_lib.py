@@ -30,6 +30,10 @@ _SIGS = {
     "edgl_last_error": (C.c_char_p, []),
     "edgl_version": (_I, []),
     "edgl_launch_count": (C.c_int64, []),
+    "edgl_num_stages": (_I, []),
+    "edgl_stage_name": (C.c_char_p, [_I]),
+    "edgl_profile": (_I, [_P, _I]),
+    "edgl_profile_read": (_I, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64), _I]),
     "edgl_create": (_I, [C.POINTER(EdglConfig), C.POINTER(_P)]),
     "edgl_destroy": (_I, [_P]),
     "edgl_get_config": (_I, [_P, C.POINTER(EdglConfig)]),
@@ -40,7 +44,7 @@ _SIGS = {
     "edgl_forward_topk_host": (_I, [_P, _P, _P, _I, _I, _P, _P, _P]),
     "edgl_encode": (_I, [_P, _P, _P, _I, _P, _P]),
     "edgl_logits_topk": (_I, [_P, _P, _P, _I, _I, _P, _P, _P]),
-    "edgl_topk_merge": (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),
+    "edgl_topk_merge": (_I, [_P, _P, _I, _I, _I, C.c_int64, _P, _P, _P]),
     "edgl_time_sinusoid_code": (_I, [_P, _I, _I, _I, _P, _P]),
     "edgl_embedding_lookup": (_I, [_P, _I, _I, _I, _I, _P, C.c_int64, _P, _P]),
     "edgl_embed": (_I, [_P, _P, _P, _I, _P, _P, _P, _P]),

@@ -36,6 +36,15 @@ struct Tensor {
   long long numel = 0;
 };
 
+// pipeline stages (one kernel launch each) for the optional CUDA-event profile (edgl_profile*)
+enum Stage {
+  ST_EMBED = 0, ST_LN_IN, ST_QKVT_GEMM, ST_ATTENTION, ST_AO_GEMM, ST_LN_ATT, ST_FF1_GEMM, ST_FF2_GEMM, ST_LN_FF,
+  ST_TR_GEMM, ST_LN_OUT, ST_LOGITS_GEMM, ST_MASK_SEEN, ST_TOPK, ST_END, ST_COUNT
+};
+const char* const kStageNames[ST_COUNT] = {"embed", "ln_in", "qkvt_gemm", "attention", "ao_gemm", "ln_att",
+                                           "ff1_gemm", "ff2_gemm", "ln_ff", "tr_gemm", "ln_out", "logits_gemm",
+                                           "mask_seen", "topk", "end"};
+
 }  // namespace edgl
 
 using namespace edgl;
@@ -68,9 +77,22 @@ struct edgl_handle {
   int32_t* st_idx = nullptr;
   float* st_val = nullptr;
   std::vector<void*> owned;
+  // optional per-stage CUDA-event profile
+  bool prof_on = false;
+  std::vector<cudaEvent_t> prof_ev;
+  std::vector<int> prof_stage;
+  size_t prof_n = 0;
 };
 
 namespace {
+
+// record an event BEFORE the stage's kernel is enqueued; the time to the next mark belongs to `stage`
+inline void mark(edgl_handle* h, int stage, cudaStream_t st) {
+  if (!h->prof_on || h->prof_n >= h->prof_ev.size()) return;
+  cudaEventRecord(h->prof_ev[h->prof_n], st);
+  h->prof_stage[h->prof_n] = stage;
+  ++h->prof_n;
+}
 
 template <typename T>
 int dev_alloc(edgl_handle* h, T** p, size_t n) {
@@ -194,11 +216,13 @@ int encode_easydgl(edgl_handle* h, const int64_t* ids, const float* ts, int B, f
   const long long rows = (long long)B * L;
   EmbedArgs e = embed_args(h, ids, ts, B);
   e.Xa = h->xa; e.ldxa = h->Ka; e.spans = h->spans; e.marks = h->marks; e.kmask = h->kmask;
+  mark(h, ST_EMBED, st);
   EDGL_TRY(launch_embed(e, st));
   const float* cur = h->xa;
   int ldcur = h->Ka;
   for (int i = 0; i < h->cfg.num_blocks; ++i) {
     const auto& w = h->bt[i];
+    mark(h, ST_QKVT_GEMM, st);
     if (i == 0) {
       // QKVT = X0 @ W + b with the position / mark-code thirds of X0 folded (commit()): temporal.py:409
       GemmArgs g;
@@ -210,18 +234,27 @@ int encode_easydgl(edgl_handle* h, const int64_t* ids, const float* ts, int B, f
                      nullptr, 0, st));
     }
     AttnArgs a = attn_args(h, w, h->qkvt, h->kmask, h->spans, h->marks, cur, ldcur, h->p0, nullptr, B, false, true);
+    mark(h, ST_ATTENTION, st);
     EDGL_TRY(launch_attention(a, st));                                                   // temporal.py:412-447
+    mark(h, ST_AO_GEMM, st);
     EDGL_TRY(dense(h->p0, d, F(w, "ao_w"), d, F(w, "ao_b"), h->p1, d, rows, d, d, ACT_NONE, cur, ldcur, st));  // :113,116
+    mark(h, ST_LN_ATT, st);
     EDGL_TRY(launch_layernorm(h->p1, F(w, "ao_ln_g"), F(w, "ao_ln_b"), B, L, d, h->p0, false, st));            // :116
+    mark(h, ST_FF1_GEMM, st);
     EDGL_TRY(dense(h->p0, d, F(w, "ff1_w"), 2 * d, F(w, "ff1_b"), h->p2, 2 * d, rows, 2 * d, d, ACT_GELU, nullptr, 0,
                    st));                                                                 // :120-121
+    mark(h, ST_FF2_GEMM, st);
     EDGL_TRY(dense(h->p2, 2 * d, F(w, "ff2_w"), d, F(w, "ff2_b"), h->p1, d, rows, d, 2 * d, ACT_NONE, h->p0, d, st));  // :125,128
+    mark(h, ST_LN_FF, st);
     EDGL_TRY(launch_layernorm(h->p1, F(w, "ff_ln_g"), F(w, "ff_ln_b"), B, L, d, h->p2, false, st));            // :128
     cur = h->p2;
     ldcur = d;
   }
+  mark(h, ST_TR_GEMM, st);
   EDGL_TRY(dense(cur, ldcur, F(h->mt, "tr_w"), d, F(h->mt, "tr_b"), h->p0, d, rows, d, d, ACT_GELU, nullptr, 0, st));  // :138
+  mark(h, ST_LN_OUT, st);
   EDGL_TRY(launch_layernorm(h->p0, F(h->mt, "tr_ln_g"), F(h->mt, "tr_ln_b"), B, L, d, y, true, st));  // :139,146
+  mark(h, ST_END, st);
   return 0;
 }
 
@@ -231,24 +264,33 @@ int encode_ctsma(edgl_handle* h, const int64_t* ids, const float* ts, int B, flo
   const long long rows = (long long)B * L;
   EmbedArgs e = embed_args(h, ids, ts, B);
   e.X0 = h->p2; e.ldx0 = 2 * d; e.spans = h->spans; e.marks = h->marks; e.kmask = h->kmask;
+  mark(h, ST_EMBED, st);
   EDGL_TRY(launch_embed(e, st));
   float* cur = h->p2;
   int cin = 2 * d;
   for (int i = 0; i < h->cfg.num_blocks; ++i) {
     const auto& w = h->bt[i];
+    mark(h, ST_LN_IN, st);
     EDGL_TRY(launch_layernorm(cur, F(w, "ln1_g"), F(w, "ln1_b"), B, L, cin, h->p0, false, st));  // CTSMA.py:68
+    mark(h, ST_QKVT_GEMM, st);
     EDGL_TRY(dense(h->p0, cin, F(w, "q_w"), d, F(w, "q_b"), h->qkvt, 4 * d, rows, d, cin, ACT_NONE, nullptr, 0, st));
     EDGL_TRY(dense(cur, cin, h->wkvt[i], 3 * d, h->bkvt[i], h->qkvt + d, 4 * d, rows, 3 * d, cin, ACT_NONE, nullptr,
                    0, st));                                                              // temporal.py:340-343
     AttnArgs a = attn_args(h, w, h->qkvt, h->kmask, h->spans, h->marks, h->p0, cin, h->p1, nullptr, B, true, false);
+    mark(h, ST_ATTENTION, st);
     EDGL_TRY(launch_attention(a, st));                                                   // temporal.py:345-385
+    mark(h, ST_LN_ATT, st);
     EDGL_TRY(launch_layernorm(h->p1, F(w, "ln2_g"), F(w, "ln2_b"), B, L, d, h->p0, false, st));  // CTSMA.py:73
+    mark(h, ST_FF1_GEMM, st);
     EDGL_TRY(dense(h->p0, d, F(w, "ff1_w"), d, F(w, "ff1_b"), h->p1, d, rows, d, d, ACT_RELU, nullptr, 0, st));  // Base.py:79
+    mark(h, ST_FF2_GEMM, st);
     EDGL_TRY(dense(h->p1, d, F(w, "ff2_w"), d, F(w, "ff2_b"), h->p2, d, rows, d, d, ACT_NONE, h->p0, d, st));    // Base.py:83,86
     cur = h->p2;
     cin = d;
   }
+  mark(h, ST_LN_OUT, st);
   EDGL_TRY(launch_layernorm(cur, F(h->mt, "out_ln_g"), F(h->mt, "out_ln_b"), B, L, d, y, true, st));  // CTSMA.py:80,87
+  mark(h, ST_END, st);
   return 0;
 }
 
@@ -273,11 +315,16 @@ int logits_topk(edgl_handle* h, const float* y, const int64_t* seen, int seen_le
   const int Ns = (int)(h->c1 - h->c0);
   for (long long r0 = 0; r0 < Bt; r0 += h->ws_rows) {
     const long long rc = (Bt - r0 < h->ws_rows) ? (Bt - r0) : h->ws_rows;
+    mark(h, ST_LOGITS_GEMM, st);
     EDGL_TRY(logits_rows(h, y + r0 * h->d, rc, h->logits_ws, Ns, st));
-    if (seen)
+    if (seen) {
+      mark(h, ST_MASK_SEEN, st);
       EDGL_TRY(launch_mask_seen(h->logits_ws, Ns, (int)rc, seen + r0 * seen_len, seen_len, h->c0, h->c1, st));
+    }
+    mark(h, ST_TOPK, st);
     EDGL_TRY(launch_topk(h->logits_ws, Ns, (int)rc, Ns, h->K, (int)h->c0, idx + r0 * h->K, val + r0 * h->K, st));
   }
+  mark(h, ST_END, st);
   return 0;
 }
 
@@ -378,6 +425,7 @@ int edgl_create(const edgl_config* cfg, edgl_handle** out) {
 int edgl_destroy(edgl_handle* h) {
   if (!h) return 0;
   for (void* p : h->owned) cudaFree(p);
+  for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
   delete h;
   return 0;
 }
@@ -385,6 +433,39 @@ int edgl_destroy(edgl_handle* h) {
 int edgl_get_config(const edgl_handle* h, edgl_config* out) {
   if (!h || !out) return set_error(EDGL_EINVAL, "null argument");
   *out = h->cfg;
+  return 0;
+}
+
+int edgl_num_stages(void) { return ST_COUNT - 1; }
+const char* edgl_stage_name(int stage) { return (stage >= 0 && stage < ST_COUNT) ? kStageNames[stage] : ""; }
+
+int edgl_profile(edgl_handle* h, int enable) {
+  if (!h) return set_error(EDGL_EINVAL, "null handle");
+  if (enable && h->prof_ev.empty()) {
+    h->prof_ev.resize(32768);
+    h->prof_stage.assign(32768, ST_END);
+    for (auto& e : h->prof_ev) EDGL_CUDA(cudaEventCreate(&e));
+  }
+  h->prof_on = enable != 0;
+  h->prof_n = 0;
+  return 0;
+}
+
+int edgl_profile_read(edgl_handle* h, double* ms, int64_t* count, int n) {
+  if (!h || !ms || !count) return set_error(EDGL_EINVAL, "null argument");
+  EDGL_REQUIRE(n >= ST_COUNT - 1, "edgl_profile_read: need room for %d stages", ST_COUNT - 1);
+  for (int i = 0; i < n; ++i) { ms[i] = 0.0; count[i] = 0; }
+  if (h->prof_n == 0) return 0;
+  EDGL_CUDA(cudaEventSynchronize(h->prof_ev[h->prof_n - 1]));
+  for (size_t i = 0; i + 1 < h->prof_n; ++i) {
+    const int s = h->prof_stage[i];
+    if (s == ST_END) continue;
+    float t = 0.f;
+    EDGL_CUDA(cudaEventElapsedTime(&t, h->prof_ev[i], h->prof_ev[i + 1]));
+    ms[s] += t;
+    count[s] += 1;
+  }
+  h->prof_n = 0;
   return 0;
 }
 
@@ -488,7 +569,10 @@ int edgl_forward_logits(edgl_handle* h, const int64_t* seqs_i, const float* seqs
   if (B == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   EDGL_TRY(encode(h, seqs_i, seqs_t, B, h->y, st));
-  return logits_rows(h, h->y, B, logits, (int)(h->c1 - h->c0), st);
+  mark(h, ST_LOGITS_GEMM, st);
+  EDGL_TRY(logits_rows(h, h->y, B, logits, (int)(h->c1 - h->c0), st));
+  mark(h, ST_END, st);
+  return 0;
 }
 
 int edgl_forward_topk(edgl_handle* h, const int64_t* seqs_i, const float* seqs_t, int B, int mask_seen,
@@ -526,11 +610,11 @@ int edgl_logits_topk(edgl_handle* h, const float* y, const int64_t* seen_ids, in
   return logits_topk(h, y, seen_ids, seen_len, Bt, cand_idx, cand_val, (cudaStream_t)stream);
 }
 
-int edgl_topk_merge(const float* cand_val, const int32_t* cand_idx, int G, int Bt, int K, int32_t* idx, float* val,
-                    void* stream) {
+int edgl_topk_merge(const float* cand_val, const int32_t* cand_idx, int G, int Bt, int K, int64_t shard_stride,
+                    int32_t* idx, float* val, void* stream) {
   if (!cand_val || !cand_idx || !idx || !val) return set_error(EDGL_EINVAL, "null argument");
-  EDGL_REQUIRE(Bt >= 0, "negative batch");
-  return launch_topk_merge(cand_val, cand_idx, G, Bt, K, idx, val, (cudaStream_t)stream);
+  EDGL_REQUIRE(Bt >= 0 && shard_stride >= 0, "negative batch or stride");
+  return launch_topk_merge(cand_val, cand_idx, G, Bt, K, shard_stride, idx, val, (cudaStream_t)stream);
 }
 
 int edgl_time_sinusoid_code(const float* ts, int B, int L, int d, float* out, void* stream) {

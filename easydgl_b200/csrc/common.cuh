@@ -115,7 +115,7 @@ int launch_mask_seen(float* logits, int ld, int B, const int64_t* ids, int seen_
                      long long col1, cudaStream_t st);
 int launch_topk(const float* logits, int ld, int B, int N, int K, int col_offset, int32_t* idx, float* val,
                 cudaStream_t st);
-int launch_topk_merge(const float* cand_val, const int32_t* cand_idx, int G, int Bt, int K, int32_t* idx,
-                      float* val, cudaStream_t st);
+int launch_topk_merge(const float* cand_val, const int32_t* cand_idx, int G, int Bt, int K, long long shard_stride,
+                      int32_t* idx, float* val, cudaStream_t st);
 
 }  // namespace edgl

@@ -181,9 +181,10 @@ int launch_topk(const float* logits, int ld, int B, int N, int K, int col_offset
   return 0;
 }
 
-// merge: cand_* are [G][Bt][K]; entries with idx < 0 are padding.
+// merge: shard g's [Bt][K] block starts at cand_*[g * shard_stride]; entries with idx < 0 are padding.
 __global__ void __launch_bounds__(256) topk_merge_kernel(const float* __restrict__ cv, const int32_t* __restrict__ ci,
-                                                         int G, int Bt, int K, int KP, int32_t* __restrict__ idx_out,
+                                                         int G, int Bt, int K, int KP, long long shard_stride,
+                                                         int32_t* __restrict__ idx_out,
                                                          float* __restrict__ val_out) {
   extern __shared__ __align__(16) unsigned long long cand[];
   const int row = blockIdx.x;
@@ -191,7 +192,7 @@ __global__ void __launch_bounds__(256) topk_merge_kernel(const float* __restrict
     unsigned long long c = 0ull;
     if (i < G * K) {
       const int g = i / K, j = i % K;
-      const long long o = ((long long)g * Bt + row) * K + j;
+      const long long o = (long long)g * shard_stride + (long long)row * K + j;
       const int32_t id = ci[o];
       if (id >= 0) c = compose(f2key(cv[o]), (uint32_t)id);
     }
@@ -211,15 +212,16 @@ __global__ void __launch_bounds__(256) topk_merge_kernel(const float* __restrict
   }
 }
 
-int launch_topk_merge(const float* cand_val, const int32_t* cand_idx, int G, int Bt, int K, int32_t* idx,
-                      float* val, cudaStream_t st) {
+int launch_topk_merge(const float* cand_val, const int32_t* cand_idx, int G, int Bt, int K, long long shard_stride,
+                      int32_t* idx, float* val, cudaStream_t st) {
+  if (shard_stride == 0) shard_stride = (long long)Bt * K;
   EDGL_REQUIRE(G >= 1 && K >= 1 && (long long)G * K <= 16384, "topk_merge: G*K must be <= 16384");
   if (Bt == 0) return 0;
   const int KP = next_pow2(G * K);
   auto kern = topk_merge_kernel;
   const size_t smem = (size_t)KP * 8;
   if (smem > 48 * 1024) EDGL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<Bt, 256, smem, st>>>(cand_val, cand_idx, G, Bt, K, KP, idx, val);
+  kern<<<Bt, 256, smem, st>>>(cand_val, cand_idx, G, Bt, K, KP, shard_stride, idx, val);
   EDGL_LAUNCH_CHECK();
   return 0;
 }

@@ -96,6 +96,18 @@ class Engine:
         except Exception:
             pass
 
+    # ------------------------------------------------------------------ profiling
+    def profile(self, enable: bool):
+        check(self.lib.edgl_profile(self._handle, int(bool(enable))))
+
+    def profile_read(self) -> Dict[str, Tuple[float, int]]:
+        """{stage: (summed device ms, launches)} since the last read (CUDA events on the launch stream)."""
+        n = self.lib.edgl_num_stages()
+        ms = (C.c_double * n)()
+        cnt = (C.c_int64 * n)()
+        check(self.lib.edgl_profile_read(self._handle, ms, cnt, n))
+        return {self.lib.edgl_stage_name(i).decode(): (ms[i], cnt[i]) for i in range(n) if cnt[i] > 0}
+
     # ------------------------------------------------------------------ model-level
     def _inputs(self, seqs_i, seqs_t) -> Tuple[torch.Tensor, torch.Tensor, int]:
         seqs_i = _req(seqs_i, torch.int64, "seqs_i", self.device)
@@ -155,7 +167,7 @@ class Engine:
             check(self.lib.edgl_encode(self._handle, seqs_i.data_ptr(), seqs_t.data_ptr(), B, y.data_ptr(), _stream()))
         return y
 
-    def logits_topk(self, y, seen_ids=None):
+    def logits_topk(self, y, seen_ids=None, out=None):
         """Local top-K of this handle's item shard for rows ``y`` [Bt,d]; global column ids."""
         y = _req(y, torch.float32, "y", self.device)
         Bt = int(y.shape[0])
@@ -163,8 +175,11 @@ class Engine:
         if seen_ids is not None:
             seen_ids = _req(seen_ids, torch.int64, "seen_ids", self.device)
             seen_len = int(seen_ids.shape[1])
-        idx = torch.empty((Bt, self.K), dtype=torch.int32, device=self.device)
-        val = torch.empty((Bt, self.K), dtype=torch.float32, device=self.device)
+        if out is None:
+            idx = torch.empty((Bt, self.K), dtype=torch.int32, device=self.device)
+            val = torch.empty((Bt, self.K), dtype=torch.float32, device=self.device)
+        else:
+            idx, val = out
         with torch.cuda.device(self.device):
             check(self.lib.edgl_logits_topk(self._handle, y.data_ptr(), _ptr(seen_ids), seen_len, Bt,
                                             idx.data_ptr(), val.data_ptr(), _stream()))
@@ -217,15 +232,19 @@ class Engine:
 # ---------------------------------------------------------------------- handle-free ops
 def topk_merge(cand_val: torch.Tensor, cand_idx: torch.Tensor):
     """[G,Bt,K] per-shard candidates -> merged (idx [Bt,K] int32, val [Bt,K]); ties -> lower id."""
-    lib = _lib.load()
     cand_val = _req(cand_val, torch.float32, "cand_val")
     cand_idx = _req(cand_idx, torch.int32, "cand_idx")
     G, Bt, K = cand_val.shape
-    idx = torch.empty((Bt, K), dtype=torch.int32, device=cand_val.device)
-    val = torch.empty((Bt, K), dtype=torch.float32, device=cand_val.device)
-    with torch.cuda.device(cand_val.device):
-        check(lib.edgl_topk_merge(cand_val.data_ptr(), cand_idx.data_ptr(), G, Bt, K, idx.data_ptr(), val.data_ptr(),
-                                  _stream()))
+    return topk_merge_raw(cand_val.data_ptr(), cand_idx.data_ptr(), G, Bt, K, 0, cand_val.device)
+
+
+def topk_merge_raw(val_ptr: int, idx_ptr: int, G: int, Bt: int, K: int, shard_stride: int, device):
+    """Merge with explicit base pointers / shard stride (used on the packed all-gather buffer)."""
+    lib = _lib.load()
+    idx = torch.empty((Bt, K), dtype=torch.int32, device=device)
+    val = torch.empty((Bt, K), dtype=torch.float32, device=device)
+    with torch.cuda.device(device):
+        check(lib.edgl_topk_merge(val_ptr, idx_ptr, G, Bt, K, shard_stride, idx.data_ptr(), val.data_ptr(), _stream()))
     return idx, val
 
 

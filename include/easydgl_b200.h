@@ -65,6 +65,15 @@ int edgl_version(void);
 /* Number of CUDA kernels this library has launched in this process (bench.py's gpu_launches). */
 int64_t edgl_launch_count(void);
 
+/* Optional per-stage device timing (no reference counterpart; the reference has no profiler).
+ * While enabled, a CUDA event is recorded on the caller's stream before every kernel of the pipeline;
+ * edgl_profile_read synchronises on the last event and returns, per stage, the summed device time (ms)
+ * and the launch count since the last read.  Stage ids are 0..edgl_num_stages()-1. */
+int edgl_num_stages(void);
+const char* edgl_stage_name(int stage);
+int edgl_profile(edgl_handle* h, int enable);
+int edgl_profile_read(edgl_handle* h, double* ms, int64_t* count, int n);
+
 /* Model(num_items, FLAGS) - EasyDGL.py:37 / CTSMA.py:22.  Uses the current CUDA device. */
 int edgl_create(const edgl_config* cfg, edgl_handle** out);
 int edgl_destroy(edgl_handle* h);
@@ -109,9 +118,10 @@ int edgl_encode(edgl_handle* h, const int64_t* seqs_i, const float* seqs_t, int 
  * with seen_ids int64 [Bt,seen_len] (may be NULL), local top-K with GLOBAL column ids. */
 int edgl_logits_topk(edgl_handle* h, const float* y, const int64_t* seen_ids, int seen_len, int Bt,
                      int32_t* cand_idx, float* cand_val, void* stream);
-/* K-way merge of G per-shard candidate lists [G,Bt,K] -> [Bt,K]; ties -> lower global index (Base.py:181). */
-int edgl_topk_merge(const float* cand_val, const int32_t* cand_idx, int G, int Bt, int K, int32_t* idx,
-                    float* val, void* stream);
+/* K-way merge of G per-shard candidate lists -> [Bt,K]; ties -> lower global index (Base.py:181).
+ * Shard g's rows start at cand_*[g * shard_stride] (elements; 0 means dense [G,Bt,K]); idx < 0 = padding. */
+int edgl_topk_merge(const float* cand_val, const int32_t* cand_idx, int G, int Bt, int K, int64_t shard_stride,
+                    int32_t* idx, float* val, void* stream);
 
 /* ---- layer-level entry points (one per reference layer, for unit parity) ---- */
 /* C.TimeSinusoidCoding(d).code(ts)  (coding.py:132-149): ts fp32 [B,L] already scaled -> [B,L,d]. */

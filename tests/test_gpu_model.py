@@ -34,14 +34,21 @@ def _check_model(name, batch, mode="parity", k=100, **over):
     ref64 = O.forward(ids, ts, W, cfg, dtype=torch.float64)
     ref32 = O.forward(ids, ts, W, cfg, dtype=torch.float32)
     assert torch.equal(logits[:, 0], torch.full((batch,), -1000.0)), "column 0 must be exactly -1000 (Q11)"
-    e64 = assert_close(logits[:, 1:], ref64[:, 1:], 1e-3, name + " logits vs fp64 oracle")
-    e32 = assert_close(logits[:, 1:], ref32[:, 1:], 1e-3, name + " logits vs fp32 oracle")
+    assert torch.isfinite(logits).all()
+    # Rows on which the reference ITSELF is ill-conditioned are excluded from the tolerance check:
+    # e.g. an all-padding CTSMA row with zero biases makes LayerNorm's input constant (variance = rounding
+    # noise, Base.py:51-56), so the fp32 and fp64 oracles disagree by O(1) there.  A row is "well-posed"
+    # when the fp32 and fp64 oracles agree to 1e-4.
+    well = (ref32.double() - ref64)[:, 1:].abs().amax(1) <= 1e-4 * ref64[:, 1:].abs().max()
+    assert int(well.sum()) >= batch - 3, "too many ill-conditioned rows: %s" % well
+    e64 = assert_close(logits[well, 1:], ref64[well, 1:], 1e-3, name + " logits vs fp64 oracle")
+    e32 = assert_close(logits[well, 1:], ref32[well, 1:], 1e-3, name + " logits vs fp32 oracle")
     # ranking
     idx, val = eng.forward_topk(ids.to(DEV), ts.to(DEV), mask_seen=True)
     idx, val = idx.cpu().long(), val.cpu()
     masked64 = O.mask_seen_logits(ref64, ids)
-    abs_err = float((logits.double() - ref64).abs().max())
-    res = O.topk_set_compare(idx, masked64, k, tau=4 * abs_err)
+    abs_err = float((logits.double() - ref64)[well].abs().max())
+    res = O.topk_set_compare(idx[well], masked64[well], k, tau=4 * abs_err)
     # the returned values are the masked logits of the returned indices, sorted, ties by index
     mine = O.mask_seen_logits(logits, ids)
     assert torch.equal(val, torch.gather(mine, 1, idx)), "top-K values must be the kernel's own masked logits"
@@ -52,7 +59,7 @@ def _check_model(name, batch, mode="parity", k=100, **over):
     _, lit = O.eval_topk(ref64, ids, True, k, rank_on="probs")
     _, lg = O.eval_topk(ref64, ids, True, k, rank_on="logits")
     finite = torch.isfinite(torch.gather(masked64, 1, lg)).all(dim=1)
-    _log(name, dict(batch=batch, rel_err_fp64=e64, rel_err_fp32=e32, abs_err=abs_err, topk=res,
+    _log(name, dict(batch=batch, well_posed_rows=int(well.sum()), rel_err_fp64=e64, rel_err_fp32=e32, abs_err=abs_err, topk=res,
                     probs_vs_logits_rank_equal=bool(torch.equal(lit[finite], lg[finite]))))
     return eng, cfg, inp, W, logits, idx, val
 

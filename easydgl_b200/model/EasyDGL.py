@@ -1,0 +1,23 @@
+"""Facade of ``src/model/EasyDGL.py``: ``EasyDGL(num_items, FLAGS)`` and
+``model(features, is_training=False) -> logits [B, num_items+1]`` (EasyDGL.py:37-151)."""
+from __future__ import annotations
+
+from .Base import Sequential
+
+
+class EasyDGL(Sequential):
+    _model = "EasyDGL"
+
+    def __init__(self, num_items, FLAGS, weights=None, mark_table=None, device="cuda:0", max_batch=512):
+        super().__init__(num_items, FLAGS)
+        self._raw_items = num_items
+        self.mask = num_items          # EasyDGL.py:39
+        self.seqslen += 1              # EasyDGL.py:40
+        self.num_items += 1            # EasyDGL.py:41
+        self.masklen = getattr(FLAGS, "masklen", 6)
+        self.time_scale = getattr(FLAGS, "time_scale", 1.0)
+        self.ct_reg = getattr(FLAGS, "ct_reg", 0.)
+        self._setup(FLAGS, weights, mark_table, device, max_batch)
+
+    def __call__(self, features, is_training):
+        return self._forward(features, is_training)

@@ -1,0 +1,63 @@
+"""Facade of the reference's ``src/module/coding.py`` layers that sit on the hot path.
+
+Same class names, ctor arguments and call signatures (coding.py:45-79,125-149); torch CUDA
+tensors stand in for TF tensors and the arithmetic runs in libeasydgl_b200.so.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .. import engine as _E
+
+
+def _glorot(shape, gen=None):
+    lim = float(np.sqrt(6.0 / (shape[0] + shape[1])))
+    return (torch.rand(shape, generator=gen) * 2 - 1) * lim
+
+
+class Embedding(object):
+    """coding.py:45-64.  ``lookup_table`` is the (zero-padded) table like the reference attribute."""
+
+    def __init__(self, vocab_size, num_units, l2_reg=0., zero_pad=True, scale=True, initializer=None,
+                 scope="embedding", device="cuda:0"):
+        self._num_units = num_units
+        self._scale = scale
+        self._zero_pad = zero_pad
+        table = initializer if torch.is_tensor(initializer) else _glorot((vocab_size, num_units))
+        table = table.to(device=device, dtype=torch.float32).contiguous()
+        if zero_pad:  # coding.py:56-57
+            table = torch.cat((torch.zeros(1, num_units, device=table.device), table[1:, :]), 0)
+        self.lookup_table = table
+
+    def __call__(self, inputs):
+        # zero_pad already applied to lookup_table; scale = x * num_units ** 0.5 (coding.py:61-63)
+        return _E.embedding_lookup(self.lookup_table, inputs, False, self._scale)
+
+
+class PositionCoding(object):
+    """coding.py:67-79."""
+
+    def __init__(self, vocab_size, num_units, l2_reg=0., initializer=None, scope="coding/pos", device="cuda:0"):
+        self.pembs = Embedding(vocab_size, num_units, l2_reg, zero_pad=False, initializer=initializer, scale=False,
+                               device=device)
+
+    def __call__(self, inputs, **kwargs):
+        return torch.cat([inputs, self.code(inputs)], dim=-1)
+
+    def code(self, inputs):
+        batch_size, seqs_len = inputs.shape[0], inputs.shape[1]
+        pos = torch.arange(seqs_len, device=inputs.device, dtype=torch.int64).unsqueeze(0).repeat(batch_size, 1)
+        return self.pembs(pos)
+
+
+class TimeSinusoidCoding(object):
+    """coding.py:125-149."""
+
+    def __init__(self, num_units):
+        self.num_units = num_units
+        self.scale = np.power(10000, np.arange(0, num_units, 2) * 1. / num_units).astype(np.float32)
+
+    def code(self, inputs):
+        assert inputs.dim() == 2, "the tensor rank should be 2."  # coding.py:139
+        return _E.time_sinusoid_code(inputs.to(torch.float32), self.num_units)

@@ -69,7 +69,7 @@ class ShardedRanker:
         eng.logits_topk(y_all, seen_all, out=(cand[0], cand[1].view(torch.float32)))
         # ---- exchange 2: all-gather of the per-shard top-K
         allc = self._buf("allcand", (G, 2, G * B, K), torch.int32, dev)
-        dist.all_gather_into_tensor(allc, cand, group=self.group)
+        dist.all_gather_into_tensor(allc.view(G * 2, G * B, K), cand, group=self.group)  # concat along dim 0
         # ---- merge this rank's rows [rank*B, (rank+1)*B) out of every shard's candidate block
         return self.merge_fn(allc, self.rank * B, B)
 

@@ -1,0 +1,86 @@
+"""The reference-facing facade: same class names / ctor args / call signatures as the reference's
+model and layer classes, checked against the oracle the way a reference test would."""
+from types import SimpleNamespace
+
+import pytest
+import torch
+
+from helpers import O, assert_close, case, synth
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _flags(cfg, **kw):
+    return SimpleNamespace(model=cfg.model, num_items=cfg.num_items, num_units=cfg.num_units, num_heads=cfg.num_heads,
+                           num_blocks=cfg.num_blocks, seqslen=cfg.seqslen, time_scale=cfg.time_scale, masklen=6,
+                           hidden_dropout_rate=0.1, attention_probs_dropout_rate=0.1, learning_rate=5e-4, l2_reg=1e-4,
+                           ct_reg=1e-7, num_train_steps=None, num_warmup_steps=None, mark=None, mask_seen=True, **kw)
+
+
+@pytest.mark.parametrize("name", ["easy_b", "ctsma_b"])
+def test_util_ranking_model_call_and_eval(name):
+    from easydgl_b200.util import ranking
+    cfg, inp, W = case(name, batch=8)
+    model = ranking(_flags(cfg), weights=W, mark_table=W["mark_table"].numpy(), device=DEV)
+    assert model.num_items == cfg.num_rows and model.num_events == cfg.num_events
+    features = {"seqs_i": inp["seqs_i"].to(DEV), "seqs_t": inp["seqs_t"].to(DEV)}
+    logits = model(features, is_training=False)
+    ref = O.forward(inp["seqs_i"], inp["seqs_t"], W, cfg, dtype=torch.float64)
+    assert_close(logits.cpu()[:, 1:], ref[:, 1:], 1e-3, "facade logits")
+    labels = torch.stack([inp["labels"]] * 2, dim=1)  # labels[:, -1] is the target (Base.py:169)
+    metrics, idx = model.eval(features, labels, mask_seen=True)
+    _, ridx = O.eval_topk(ref, inp["seqs_i"], True, 100, rank_on="probs")
+    want = O.ranking_metrics(ridx, inp["labels"])
+    res = O.topk_set_compare(idx.cpu().long(), O.mask_seen_logits(ref, inp["seqs_i"]), 100,
+                             tau=4 * float((logits.cpu().double() - ref).abs().max()))
+    assert res["bad"] == 0
+    if res["exact"] == res["rows"]:
+        for k, v in want.items():
+            assert abs(metrics[k] - v) < 1e-9, (k, metrics[k], v)
+    # streaming means (tf.metrics.mean) and reset (metric_init_op)
+    m2, _ = model.eval(features, labels, mask_seen=True)
+    assert all(abs(m2[k] - metrics[k]) < 1e-12 for k in metrics)
+    model.reset_metrics()
+    with pytest.raises(NotImplementedError):
+        model.train(features, labels)
+    with pytest.raises(NotImplementedError):
+        ranking(SimpleNamespace(model="SASREC", num_items=10))
+
+
+def test_bimau_layer_facade_signature():
+    """T.BiMAU(num_units, num_heads, num_events, dropout)(queries, keys, masks, intervals, marks, is_training)."""
+    from easydgl_b200.module import temporal as T
+    cfg, inp, W = case("easy_b", batch=4)
+    W64 = O._cast(W, torch.float64)
+    X0, kmask, spans, marks = O.easydgl_inputs(inp["seqs_i"], inp["seqs_t"], W64, cfg, torch.float64)
+    blk = W["blocks"][0]
+    keep = {k: blk[k] for k in ("qkvt_w", "qkvt_b", "int_w", "int_b", "int_weight", "int_scaling")}
+    layer = T.BiMAU(cfg.num_units, cfg.num_heads, cfg.num_events, 0.1, weights=keep, device=DEV)
+    masks = kmask.float().unsqueeze(1).repeat(cfg.num_heads, cfg.L, 1).to(DEV)   # EasyDGL.py:94-95
+    out, lam = layer(X0.float().to(DEV), X0.float().to(DEV), masks, spans.float().to(DEV), marks.to(DEV), False)
+    rO, rl = O.bimau(X0, kmask, spans, marks, W64["blocks"][0], cfg.num_units, cfg.num_heads, cfg.num_events)
+    assert_close(out.cpu(), rO, 1e-4, "BiMAU facade out")
+    assert_close(lam.cpu(), rl, 1e-4, "BiMAU facade lam")
+    assert lam.shape == (cfg.num_heads * 4, cfg.L, cfg.num_events)
+    G, lam2 = layer.intensity(torch.randn(cfg.num_heads * 4, cfg.L, cfg.num_units // cfg.num_heads, device=DEV),
+                              spans.float().to(DEV), marks.to(DEV))
+    assert G.shape == (cfg.num_heads * 4, cfg.L, cfg.L)
+
+
+def test_coding_layer_facades():
+    from easydgl_b200.module import coding as C
+    g = torch.Generator().manual_seed(3)
+    table = torch.randn(40, 16, generator=g)
+    emb = C.Embedding(40, 16, 0.0, zero_pad=True, scale=True, initializer=table, scope="item_embs", device=DEV)
+    ids = torch.randint(0, 40, (3, 7), generator=g)
+    assert torch.equal(emb(ids.to(DEV)).cpu(), O.embedding(O.zero_pad_table(table), ids, True, 16))
+    assert torch.equal(emb.lookup_table[0].cpu(), torch.zeros(16))
+    pc = C.PositionCoding(7, 16, 0.0, initializer=table[:7], device=DEV)
+    x = emb(ids.to(DEV))
+    assert pc(x).shape == (3, 7, 32) and torch.equal(pc.code(x)[1].cpu(), table[:7])
+    tc = C.TimeSinusoidCoding(16)
+    ts = torch.rand(3, 7, generator=g) * 12000
+    assert_close(tc.code(ts.to(DEV)).cpu(), O.time_sinusoid_code(ts, 16, torch.float64), 1e-5, "tcoding")
+    with pytest.raises(AssertionError):
+        tc.code(torch.zeros(2, 3, 4, device=DEV))

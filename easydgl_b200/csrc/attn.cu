@@ -7,6 +7,9 @@
 // The reference runs ~60 TF ops with [hB,L,L] and two [hB,L,L,E] HBM round trips; here one CTA owns
 // one (sequence, head): K/V/T/marks and the intensity MLP weights live in shared memory, each thread
 // owns one query row, S/P/G never leave registers.
+#include <stdlib.h>
+
+#include "attn_mma.cuh"
 #include "common.cuh"
 
 namespace edgl {
@@ -220,6 +223,19 @@ int launch_attention(const AttnArgs& a, cudaStream_t st) {
                    (a.ldo % 4 == 0) && (!a.R || a.ldr % 4 == 0),
                "attention: leading dimensions must be multiples of 4");
   if (a.B == 0) return 0;
+  // tensor-core path (attn_mma.cuh) for the shapes it is instantiated for; EDGL_ATTN=simt forces the
+  // CUDA-core kernel below (same results to fp32 rounding; used by the parity tests to cover both)
+  static const bool force_simt = [] {
+    const char* e = getenv("EDGL_ATTN");
+    return e && e[0] == 's';
+  }();
+  if (!force_simt) {
+    int r = 1;
+    if (dh == 8) r = launch_attention_mma_dh8(a, st);
+    else if (dh == 16) r = launch_attention_mma_dh16(a, st);
+    else if (dh == 32) r = launch_attention_mma_dh32(a, st);
+    if (r <= 0) return r;
+  }
 #define EDGL_ATT(DHV)                                                     \
   if (dh == DHV) {                                                        \
     if (a.E <= 16) return launch_attention_t<DHV, 16>(a, st);             \

@@ -52,6 +52,7 @@ _SIGS = {
     "edgl_intensity": (_I, [_P, _I, _P, _P, _P, _I, _P, _P, _P]),
     "edgl_layernorm": (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
     "edgl_dense": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P]),
+    "edgl_dense_nk": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P]),
     "edgl_topk": (_I, [_P, _I, _I, _P, _I, _I, _P, _P, _P]),
 }
 EXPORTS = tuple(_SIGS)

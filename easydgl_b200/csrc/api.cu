@@ -66,6 +66,10 @@ struct edgl_handle {
   float* wfold0 = nullptr;     // EasyDGL block 0: [Ka,4d]
   float* pbias0 = nullptr;     // EasyDGL block 0: [L,4d] = pos_embs @ W[d:2d] + b
   std::vector<float*> wkvt, bkvt;  // CTSMA: packed [Cin,3d], [3d]
+  // K-major ([N,K]) copies of every dense kernel for the tensor-core GEMM (made in edgl_commit)
+  float* wfold0T = nullptr;                               // [4d, Ka]
+  std::vector<std::map<std::string, float*>> btT;         // per block: name -> [N,K]
+  std::map<std::string, float*> mtT;                      // model level (tr_w)
   // workspace (owned)
   float *xa = nullptr, *p0 = nullptr, *p1 = nullptr, *p2 = nullptr, *qkvt = nullptr, *spans = nullptr, *y = nullptr,
         *logits_ws = nullptr;
@@ -184,6 +188,15 @@ int dense(const float* A, int lda, const float* W, int ldw, const float* bias, f
   return launch_gemm(g, st);
 }
 
+// dense layer with a K-major ([N,K]) kernel -> tensor-core path
+int dense_nk(const float* A, int lda, const float* Wt, int K, const float* bias, float* C, int ldc, long long M, int N,
+             int act, const float* R, int ldr, cudaStream_t st) {
+  GemmArgs g;
+  g.A = A; g.lda = lda; g.W = Wt; g.ldw = K; g.w_is_nk = true; g.C = C; g.ldc = ldc;
+  g.M = (int)M; g.N = N; g.K = K; g.bias = bias; g.act = act; g.R = R; g.ldr = ldr;
+  return launch_gemm(g, st);
+}
+
 AttnArgs attn_args(const edgl_handle* h, const std::map<std::string, Tensor>& w, const float* qkvt, const uint8_t* kmask,
                    const float* spans, const uint8_t* marks, const float* R, int ldr, float* O, float* lam, int B,
                    bool causal, bool diag_one) {
@@ -226,32 +239,33 @@ int encode_easydgl(edgl_handle* h, const int64_t* ids, const float* ts, int B, f
     if (i == 0) {
       // QKVT = X0 @ W + b with the position / mark-code thirds of X0 folded (commit()): temporal.py:409
       GemmArgs g;
-      g.A = h->xa; g.lda = h->Ka; g.W = h->wfold0; g.ldw = 4 * d; g.C = h->qkvt; g.ldc = 4 * d;
+      g.A = h->xa; g.lda = h->Ka; g.W = h->wfold0T; g.ldw = h->Ka; g.w_is_nk = true; g.C = h->qkvt; g.ldc = 4 * d;
       g.M = (int)rows; g.N = 4 * d; g.K = h->Ka; g.pbias = h->pbias0; g.pperiod = L;
       EDGL_TRY(launch_gemm(g, st));
     } else {
-      EDGL_TRY(dense(cur, ldcur, F(w, "qkvt_w"), 4 * d, F(w, "qkvt_b"), h->qkvt, 4 * d, rows, 4 * d, d, ACT_NONE,
-                     nullptr, 0, st));
+      EDGL_TRY(dense_nk(cur, ldcur, h->btT[i].at("qkvt_w"), d, F(w, "qkvt_b"), h->qkvt, 4 * d, rows, 4 * d, ACT_NONE,
+                        nullptr, 0, st));
     }
     AttnArgs a = attn_args(h, w, h->qkvt, h->kmask, h->spans, h->marks, cur, ldcur, h->p0, nullptr, B, false, true);
     mark(h, ST_ATTENTION, st);
     EDGL_TRY(launch_attention(a, st));                                                   // temporal.py:412-447
     mark(h, ST_AO_GEMM, st);
-    EDGL_TRY(dense(h->p0, d, F(w, "ao_w"), d, F(w, "ao_b"), h->p1, d, rows, d, d, ACT_NONE, cur, ldcur, st));  // :113,116
+    EDGL_TRY(dense_nk(h->p0, d, h->btT[i].at("ao_w"), d, F(w, "ao_b"), h->p1, d, rows, d, ACT_NONE, cur, ldcur, st));  // :113,116
     mark(h, ST_LN_ATT, st);
     EDGL_TRY(launch_layernorm(h->p1, F(w, "ao_ln_g"), F(w, "ao_ln_b"), B, L, d, h->p0, false, st));            // :116
     mark(h, ST_FF1_GEMM, st);
-    EDGL_TRY(dense(h->p0, d, F(w, "ff1_w"), 2 * d, F(w, "ff1_b"), h->p2, 2 * d, rows, 2 * d, d, ACT_GELU, nullptr, 0,
-                   st));                                                                 // :120-121
+    EDGL_TRY(dense_nk(h->p0, d, h->btT[i].at("ff1_w"), d, F(w, "ff1_b"), h->p2, 2 * d, rows, 2 * d, ACT_GELU, nullptr,
+                      0, st));                                                           // :120-121
     mark(h, ST_FF2_GEMM, st);
-    EDGL_TRY(dense(h->p2, 2 * d, F(w, "ff2_w"), d, F(w, "ff2_b"), h->p1, d, rows, d, 2 * d, ACT_NONE, h->p0, d, st));  // :125,128
+    EDGL_TRY(dense_nk(h->p2, 2 * d, h->btT[i].at("ff2_w"), 2 * d, F(w, "ff2_b"), h->p1, d, rows, d, ACT_NONE, h->p0, d,
+                      st));                                                              // :125,128
     mark(h, ST_LN_FF, st);
     EDGL_TRY(launch_layernorm(h->p1, F(w, "ff_ln_g"), F(w, "ff_ln_b"), B, L, d, h->p2, false, st));            // :128
     cur = h->p2;
     ldcur = d;
   }
   mark(h, ST_TR_GEMM, st);
-  EDGL_TRY(dense(cur, ldcur, F(h->mt, "tr_w"), d, F(h->mt, "tr_b"), h->p0, d, rows, d, d, ACT_GELU, nullptr, 0, st));  // :138
+  EDGL_TRY(dense_nk(cur, ldcur, h->mtT.at("tr_w"), d, F(h->mt, "tr_b"), h->p0, d, rows, d, ACT_GELU, nullptr, 0, st));  // :138
   mark(h, ST_LN_OUT, st);
   EDGL_TRY(launch_layernorm(h->p0, F(h->mt, "tr_ln_g"), F(h->mt, "tr_ln_b"), B, L, d, y, true, st));  // :139,146
   mark(h, ST_END, st);
@@ -273,18 +287,19 @@ int encode_ctsma(edgl_handle* h, const int64_t* ids, const float* ts, int B, flo
     mark(h, ST_LN_IN, st);
     EDGL_TRY(launch_layernorm(cur, F(w, "ln1_g"), F(w, "ln1_b"), B, L, cin, h->p0, false, st));  // CTSMA.py:68
     mark(h, ST_QKVT_GEMM, st);
-    EDGL_TRY(dense(h->p0, cin, F(w, "q_w"), d, F(w, "q_b"), h->qkvt, 4 * d, rows, d, cin, ACT_NONE, nullptr, 0, st));
-    EDGL_TRY(dense(cur, cin, h->wkvt[i], 3 * d, h->bkvt[i], h->qkvt + d, 4 * d, rows, 3 * d, cin, ACT_NONE, nullptr,
-                   0, st));                                                              // temporal.py:340-343
+    EDGL_TRY(dense_nk(h->p0, cin, h->btT[i].at("q_w"), cin, F(w, "q_b"), h->qkvt, 4 * d, rows, d, ACT_NONE, nullptr, 0,
+                      st));
+    EDGL_TRY(dense_nk(cur, cin, h->btT[i].at("kvt_w"), cin, h->bkvt[i], h->qkvt + d, 4 * d, rows, 3 * d, ACT_NONE,
+                      nullptr, 0, st));                                                  // temporal.py:340-343
     AttnArgs a = attn_args(h, w, h->qkvt, h->kmask, h->spans, h->marks, h->p0, cin, h->p1, nullptr, B, true, false);
     mark(h, ST_ATTENTION, st);
     EDGL_TRY(launch_attention(a, st));                                                   // temporal.py:345-385
     mark(h, ST_LN_ATT, st);
     EDGL_TRY(launch_layernorm(h->p1, F(w, "ln2_g"), F(w, "ln2_b"), B, L, d, h->p0, false, st));  // CTSMA.py:73
     mark(h, ST_FF1_GEMM, st);
-    EDGL_TRY(dense(h->p0, d, F(w, "ff1_w"), d, F(w, "ff1_b"), h->p1, d, rows, d, d, ACT_RELU, nullptr, 0, st));  // Base.py:79
+    EDGL_TRY(dense_nk(h->p0, d, h->btT[i].at("ff1_w"), d, F(w, "ff1_b"), h->p1, d, rows, d, ACT_RELU, nullptr, 0, st));  // Base.py:79
     mark(h, ST_FF2_GEMM, st);
-    EDGL_TRY(dense(h->p1, d, F(w, "ff2_w"), d, F(w, "ff2_b"), h->p2, d, rows, d, d, ACT_NONE, h->p0, d, st));    // Base.py:83,86
+    EDGL_TRY(dense_nk(h->p1, d, h->btT[i].at("ff2_w"), d, F(w, "ff2_b"), h->p2, d, rows, d, ACT_NONE, h->p0, d, st));    // Base.py:83,86
     cur = h->p2;
     cin = d;
   }
@@ -313,16 +328,17 @@ int logits_rows(edgl_handle* h, const float* y, long long rc, float* out, int ld
 int logits_topk(edgl_handle* h, const float* y, const int64_t* seen, int seen_len, long long Bt, int32_t* idx,
                 float* val, cudaStream_t st) {
   const int Ns = (int)(h->c1 - h->c0);
+  const int ldw = (Ns + 3) & ~3;  // padded pitch: vector stores in the GEMM epilogue
   for (long long r0 = 0; r0 < Bt; r0 += h->ws_rows) {
     const long long rc = (Bt - r0 < h->ws_rows) ? (Bt - r0) : h->ws_rows;
     mark(h, ST_LOGITS_GEMM, st);
-    EDGL_TRY(logits_rows(h, y + r0 * h->d, rc, h->logits_ws, Ns, st));
+    EDGL_TRY(logits_rows(h, y + r0 * h->d, rc, h->logits_ws, ldw, st));
     if (seen) {
       mark(h, ST_MASK_SEEN, st);
-      EDGL_TRY(launch_mask_seen(h->logits_ws, Ns, (int)rc, seen + r0 * seen_len, seen_len, h->c0, h->c1, st));
+      EDGL_TRY(launch_mask_seen(h->logits_ws, ldw, (int)rc, seen + r0 * seen_len, seen_len, h->c0, h->c1, st));
     }
     mark(h, ST_TOPK, st);
-    EDGL_TRY(launch_topk(h->logits_ws, Ns, (int)rc, Ns, h->K, (int)h->c0, idx + r0 * h->K, val + r0 * h->K, st));
+    EDGL_TRY(launch_topk(h->logits_ws, ldw, (int)rc, Ns, h->K, (int)h->c0, idx + r0 * h->K, val + r0 * h->K, st));
   }
   mark(h, ST_END, st);
   return 0;
@@ -371,6 +387,7 @@ int edgl_create(const edgl_config* cfg, edgl_handle** out) {
   h->c1 = h->c0 + per < h->N1 ? h->c0 + per : h->N1;
   if (h->c0 > h->c1) h->c0 = h->c1;
   h->bt.resize(cfg->num_blocks);
+  h->btT.resize(cfg->num_blocks);
   h->wkvt.assign(cfg->num_blocks, nullptr);
   h->bkvt.assign(cfg->num_blocks, nullptr);
   const long long rows = (long long)cfg->max_batch * h->L;
@@ -403,11 +420,12 @@ int edgl_create(const edgl_config* cfg, edgl_handle** out) {
   {
     const long long Ns = h->c1 - h->c0 > 0 ? h->c1 - h->c0 : 1;
     const long long max_bt = (long long)cfg->max_batch * cfg->shard_world;
-    long long r = (2ll << 30) / (Ns * 4);
+    const long long ldw = (Ns + 3) & ~3ll;
+    long long r = (2ll << 30) / (ldw * 4);
     if (r < 1) r = 1;
     if (r > max_bt) r = max_bt;
     h->ws_rows = r;
-    EDGL_ALLOC(h->logits_ws, r * Ns);
+    EDGL_ALLOC(h->logits_ws, r * ldw);
   }
   EDGL_ALLOC(h->st_ids, rows);
   EDGL_ALLOC(h->st_ts, (long long)cfg->max_batch * h->ts_len);
@@ -546,6 +564,35 @@ int edgl_commit(edgl_handle* h, void* stream) {
         EDGL_CUDA(cudaMemcpyAsync(h->bkvt[i] + j * d, F(w, bn[j]), (size_t)d * sizeof(float),
                                   cudaMemcpyDeviceToDevice, st));
       }
+    }
+  }
+  // K-major copies of the dense kernels for the tcgen05 GEMM (allocated once, refreshed on every commit)
+  {
+    auto transposed = [&](std::map<std::string, float*>& dst, const std::string& key, const float* src, int K,
+                          int N) -> int {
+      float*& buf = dst[key];
+      if (!buf) EDGL_TRY(dev_alloc(h, &buf, (size_t)K * N));
+      return launch_transpose(src, K, N, buf, st);
+    };
+    for (int i = 0; i < h->cfg.num_blocks; ++i) {
+      const auto& w = h->bt[i];
+      const int cin = cin_of(h, i);
+      if (easy) {
+        if (i > 0) EDGL_TRY(transposed(h->btT[i], "qkvt_w", F(w, "qkvt_w"), d, 4 * d));
+        EDGL_TRY(transposed(h->btT[i], "ao_w", F(w, "ao_w"), d, d));
+        EDGL_TRY(transposed(h->btT[i], "ff1_w", F(w, "ff1_w"), d, 2 * d));
+        EDGL_TRY(transposed(h->btT[i], "ff2_w", F(w, "ff2_w"), 2 * d, d));
+      } else {
+        EDGL_TRY(transposed(h->btT[i], "q_w", F(w, "q_w"), cin, d));
+        EDGL_TRY(transposed(h->btT[i], "kvt_w", h->wkvt[i], cin, 3 * d));
+        EDGL_TRY(transposed(h->btT[i], "ff1_w", F(w, "ff1_w"), d, d));
+        EDGL_TRY(transposed(h->btT[i], "ff2_w", F(w, "ff2_w"), d, d));
+      }
+    }
+    if (easy) {
+      EDGL_TRY(transposed(h->mtT, "tr_w", F(h->mt, "tr_w"), d, d));
+      if (!h->wfold0T) EDGL_TRY(dev_alloc(h, &h->wfold0T, (size_t)h->Ka * 4 * d));
+      EDGL_TRY(launch_transpose(h->wfold0, h->Ka, 4 * d, h->wfold0T, st));
     }
   }
   int flag = 0;
@@ -702,6 +749,13 @@ int edgl_dense(const float* x, const float* w, const float* b, int M, int K, int
   if (!x || !w || !out) return set_error(EDGL_EINVAL, "null argument");
   EDGL_REQUIRE(act >= 0 && act <= 2, "dense: unknown activation %d", act);
   return dense(x, K, w, N, b, out, N, M, N, K, act, nullptr, 0, (cudaStream_t)stream);
+}
+
+int edgl_dense_nk(const float* x, const float* wt, const float* b, int M, int K, int N, int act, float* out,
+                  void* stream) {
+  if (!x || !wt || !out) return set_error(EDGL_EINVAL, "null argument");
+  EDGL_REQUIRE(act >= 0 && act <= 2, "dense: unknown activation %d", act);
+  return dense_nk(x, K, wt, K, b, out, N, M, N, act, nullptr, 0, (cudaStream_t)stream);
 }
 
 int edgl_topk(float* logits, int B, int N, const int64_t* seen_ids, int seen_len, int K, int32_t* idx, float* val,

@@ -64,6 +64,9 @@ struct GemmArgs {
   bool zero_wrow0 = false;  // w_is_nk only: treat W row 0 (= output column 0) as all-zero (zero_pad table)
 };
 int launch_gemm(const GemmArgs& a, cudaStream_t st);
+bool gemm_tc_supported(const GemmArgs& a);
+int launch_gemm_tc(const GemmArgs& a, cudaStream_t st);
+int launch_transpose(const float* in, int rows, int cols, float* out, cudaStream_t st);
 
 struct EmbedArgs {
   int model;  // 0 EasyDGL, 1 CTSMA

@@ -6,6 +6,8 @@
 // TF32 rounding (2^-11 per operand) flips top-K sets (hard part 1).
 // 128x128x16 tiles, 256 threads, 8x8 register micro-tiles, register-staged double buffering.
 // Epilogue: + bias[N] + periodic bias[(m % period), N] -> activation -> + residual.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace edgl {
@@ -182,10 +184,38 @@ __global__ void __launch_bounds__(256, 2) gemm_f32_kernel(GemmArgs a, int ntn, b
   }
 }
 
+// out[c][r] = in[r][c]  (weights are transposed once at commit so the tensor-core kernel sees K-major W)
+__global__ void transpose_kernel(const float* __restrict__ in, int rows, int cols, float* __restrict__ out) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < rows && c < cols) ? in[(long long)r * cols + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (r < rows && c < cols) out[(long long)c * rows + r] = tile[threadIdx.x][i];
+  }
+}
+
+int launch_transpose(const float* in, int rows, int cols, float* out, cudaStream_t st) {
+  if (rows == 0 || cols == 0) return 0;
+  transpose_kernel<<<dim3(cdiv(cols, 32), cdiv(rows, 32)), dim3(32, 8), 0, st>>>(in, rows, cols, out);
+  EDGL_LAUNCH_CHECK();
+  return 0;
+}
+
 int launch_gemm(const GemmArgs& a, cudaStream_t st) {
   EDGL_REQUIRE(a.M >= 0 && a.N > 0 && a.K > 0, "gemm: bad shape M=%d N=%d K=%d", a.M, a.N, a.K);
   if (a.M == 0) return 0;
   EDGL_REQUIRE(!a.pbias || a.pperiod > 0, "gemm: periodic bias needs a period");
+  // Blackwell tensor-core path (gemm_tc.cu) whenever W is K-major; EDGL_GEMM=simt forces the CUDA-core kernel
+  static const bool force_simt = [] {
+    const char* e = getenv("EDGL_GEMM");
+    return e && e[0] == 's';
+  }();
+  if (!force_simt && gemm_tc_supported(a)) return launch_gemm_tc(a, st);
   const int ntn = cdiv(a.N, BN);
   const long long ntm = cdiv(a.M, BM);
   EDGL_REQUIRE(ntm * ntn < (1ll << 31), "gemm: grid too large");

@@ -1,0 +1,393 @@
+// gemm_tc.cu - Blackwell-native dense layer: tcgen05.mma (kind::tf32, accumulators in TMEM), operands
+// staged by TMA (128B swizzle) through an mbarrier pipeline, warp-specialised persistent CTAs.
+//
+// Replaces the tf.layers.dense / tied-logits matmuls of the hot path (temporal.py:409, 340-343;
+// EasyDGL.py:113,120,125,138,149; Base.py:77-87).  Arithmetic is 3xTF32:
+//     C = A_lo*W_hi + A_hi*W_lo + A_hi*W_hi,    x_hi = the 19 bits the tensor core reads, x_lo = x - x_hi
+// so the result carries fp32-level accuracy (the ranking parity bar rules out plain TF32).
+// The lo halves are produced on the fly in shared memory by four "splitter" warps (an element-wise pass
+// over the freshly landed TMA tiles - the swizzled layout is preserved because the op is element-wise),
+// so HBM/L2 only ever carry the fp32 operands once.
+//
+// Roles (384 threads, 1 CTA/SM, persistent over 128 x BN output tiles):
+//   warp 0      TMA producer            warp 1      tcgen05.mma issuer (one elected lane)
+//   warp 2      TMEM allocator          warps 4-7   epilogue: tcgen05.ld -> bias/act/residual -> global
+//   warps 8-11  splitters (A_lo, W_lo)
+// Pipelines: full[s] (TMA landed) -> split[s] (lo halves written) -> MMA -> empty[s];
+//            tmem_full[a] (tile accumulated) -> epilogue -> tmem_empty[a]  (two TMEM accumulators).
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace edgl {
+
+namespace tc {
+
+constexpr int BM = 128;      // UMMA M
+constexpr int BK = 32;       // floats per k-block = one 128-byte swizzle row
+constexpr int UK = 8;        // UMMA K for tf32 (32 bytes)
+constexpr int NTHREADS = 384;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// K-major, 128B-swizzled shared-memory operand descriptor (rows of 128 B, 8-row groups 1024 B apart)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3ffff) >> 4);       // start address >> 4, bits [0,14)
+  d |= (uint64_t)1 << 16;                        // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;              // stride byte offset: 8 rows * 128 B
+  d |= (uint64_t)1 << 46;                        // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
+  return d;
+}
+// instruction descriptor: D=f32, A=B=tf32, both K-major, M=128, N=bn
+__host__ __device__ constexpr uint32_t umma_idesc(int bn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct Params {
+  float* C; int ldc;
+  int M, N, K;
+  const float* bias;
+  const float* pbias; int pperiod;
+  const float* R; int ldr;
+  int act;
+  int col0_bias_only;  // tied zero-padded table: column 0 is exactly the bias (coding.py:56-57)
+  int ntn, num_tiles, kblocks;
+};
+
+__device__ __forceinline__ float gelu_erf_tc(float x) {
+  return x * (0.5f * (1.0f + erff(__fdiv_rn(x, 1.41421356237309504880f))));  // EasyDGL.py:31-32
+}
+
+template <int BN>
+struct Smem {
+  static constexpr int A_BYTES = BM * BK * 4;     // 16 KB
+  static constexpr int B_BYTES = BN * BK * 4;
+  static constexpr int STAGE = 2 * A_BYTES + 2 * B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 2 : 3;
+  static constexpr int BYTES = STAGES * STAGE + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(NTHREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, Params p) {
+  using SM = Smem<BN>;
+  constexpr int S = SM::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + S * SM::STAGE);
+  uint64_t* full = bars;            // [S]
+  uint64_t* split = bars + S;       // [S]
+  uint64_t* empty = bars + 2 * S;   // [S]
+  uint64_t* tfull = bars + 3 * S;   // [2]
+  uint64_t* tempty = tfull + 2;     // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  auto stA = [&](int s) { return base + s * SM::STAGE; };
+  auto stAlo = [&](int s) { return base + s * SM::STAGE + SM::A_BYTES; };
+  auto stB = [&](int s) { return base + s * SM::STAGE + 2 * SM::A_BYTES; };
+  auto stBlo = [&](int s) { return base + s * SM::STAGE + 2 * SM::A_BYTES + SM::B_BYTES; };
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < S; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&split[i], 128);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "n"(2 * BN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int KB = p.kblocks;
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapA)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapB)) : "memory");
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / p.ntn) * BM, n0 = (tile % p.ntn) * BN;
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int s = it % S;
+          mbar_wait(&empty[s], ((it / S) & 1) ^ 1);
+          mbar_expect_tx(&full[s], SM::A_BYTES + SM::B_BYTES);
+          tma_load_2d(&mapA, &full[s], stA(s), kb * BK, m0);
+          tma_load_2d(&mapB, &full[s], stB(s), kb * BK, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc(BN);
+      uint32_t it = 0, tcount = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tcount) {
+        const int acc = tcount & 1;
+        mbar_wait(&tempty[acc], ((tcount >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int s = it % S;
+          mbar_wait(&split[s], (it / S) & 1);
+          tc_fence_after();
+          const uint32_t a_hi = smem_u32(stA(s)), a_lo = smem_u32(stAlo(s));
+          const uint32_t b_hi = smem_u32(stB(s)), b_lo = smem_u32(stBlo(s));
+#pragma unroll
+          for (int k = 0; k < BK / UK; ++k) {
+            const uint32_t off = k * UK * 4;  // bytes along K inside the 128 B swizzle row
+            const uint64_t dah = umma_desc(a_hi + off), dal = umma_desc(a_lo + off);
+            const uint64_t dbh = umma_desc(b_hi + off), dbl = umma_desc(b_lo + off);
+            umma_tf32(d_tmem, dal, dbh, idesc, (kb | k) != 0);
+            umma_tf32(d_tmem, dah, dbl, idesc, 1);
+            umma_tf32(d_tmem, dah, dbh, idesc, 1);
+          }
+          umma_commit(&empty[s]);          // frees the stage when these MMAs have read it
+        }
+        umma_commit(&tfull[acc]);          // accumulator complete
+      }
+    }
+  } else if (warp >= 8) {
+    // ------------------------------------------------------------------ splitters: lo = x - tf32(x)
+    const int t = threadIdx.x - 256;  // 0..127
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int kb = 0; kb < KB; ++kb, ++it) {
+        const int s = it % S;
+        mbar_wait(&full[s], (it / S) & 1);
+        const float4* a = reinterpret_cast<const float4*>(stA(s));
+        float4* al = reinterpret_cast<float4*>(stAlo(s));
+        const float4* b = reinterpret_cast<const float4*>(stB(s));
+        float4* bl = reinterpret_cast<float4*>(stBlo(s));
+        auto lo4 = [](float4 v) {
+          float4 r;
+          r.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+          r.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+          r.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+          r.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+          return r;
+        };
+#pragma unroll 4
+        for (int i = t; i < SM::A_BYTES / 16; i += 128) al[i] = lo4(a[i]);
+#pragma unroll 4
+        for (int i = t; i < SM::B_BYTES / 16; i += 128) bl[i] = lo4(b[i]);
+        fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
+        mbar_arrive(&split[s]);
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue
+    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    const bool c_vec = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+    const bool r_vec = p.R && (p.ldr % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.R) & 15) == 0);
+    uint32_t tcount = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tcount) {
+      const int acc = tcount & 1;
+      const int m0 = (tile / p.ntn) * BM, n0 = (tile % p.ntn) * BN;
+      mbar_wait(&tfull[acc], (tcount >> 1) & 1);
+      tc_fence_after();
+      const long long row = (long long)m0 + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      const float* pb = (p.pbias && row_ok) ? p.pbias + (row % p.pperiod) * (long long)p.N : nullptr;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + acc * BN + c0 + ((uint32_t)(q * 32) << 16), r);
+        if (!row_ok || n0 + c0 >= p.N) continue;
+        float* crow = p.C + row * p.ldc + n0 + c0;
+        const float* rrow = p.R ? p.R + row * p.ldr + n0 + c0 : nullptr;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const int col = n0 + c0 + j;
+          float v[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float x = __uint_as_float(r[j + e]);
+            const int c = col + e;
+            if (c < p.N) {
+              if (p.col0_bias_only && c == 0) x = 0.f;
+              if (p.bias) x += p.bias[c];
+              if (pb) x += pb[c];
+              if (p.act == ACT_GELU) x = gelu_erf_tc(x);
+              else if (p.act == ACT_RELU) x = fmaxf(x, 0.f);
+            }
+            v[e] = x;
+          }
+          if (col + 3 < p.N && c_vec && (!p.R || r_vec)) {
+            if (rrow) {
+              const float4 rr = *reinterpret_cast<const float4*>(rrow + j);
+              v[0] += rr.x; v[1] += rr.y; v[2] += rr.z; v[3] += rr.w;
+            }
+            *reinterpret_cast<float4*>(crow + j) = make_float4(v[0], v[1], v[2], v[3]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (col + e < p.N) crow[j + e] = v[e] + (rrow ? rrow[j + e] : 0.f);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty[acc]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * BN));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      f = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(f);
+  }();
+  return fn;
+}
+
+// 2-D fp32 tensor [rows][cols] with row pitch ld floats; box = [box_rows][32 floats], 128B swizzle
+static int make_map(CUtensorMap* m, const float* ptr, long long rows, long long cols, long long ld, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return set_error(-3, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(-3, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return 0;
+}
+
+}  // namespace tc
+
+// Can this GEMM go through the tensor-core kernel?  (W must be [N,K] K-major.)
+bool gemm_tc_supported(const GemmArgs& a) {
+  if (!a.w_is_nk) return false;
+  if (a.M < 1 || a.K < 8) return false;
+  if ((a.lda % 4) || (a.ldw % 4)) return false;  // TMA: 16-byte row pitch
+  if ((reinterpret_cast<uintptr_t>(a.A) & 15) || (reinterpret_cast<uintptr_t>(a.W) & 15)) return false;
+  return true;
+}
+
+int launch_gemm_tc(const GemmArgs& a, cudaStream_t st) {
+  using namespace tc;
+  static int num_sms = [] {
+    int dev = 0, n = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n;
+  }();
+  if (a.M == 0) return 0;
+  const int bn = a.N > 128 ? 256 : 128;
+  CUtensorMap mapA, mapB;
+  EDGL_TRY(make_map(&mapA, a.A, a.M, a.K, a.lda, BM));
+  EDGL_TRY(make_map(&mapB, a.W, a.N, a.K, a.ldw, bn));
+  Params p;
+  p.C = a.C; p.ldc = a.ldc; p.M = a.M; p.N = a.N; p.K = a.K; p.bias = a.bias; p.pbias = a.pbias;
+  p.pperiod = a.pperiod > 0 ? a.pperiod : 1; p.R = a.R; p.ldr = a.ldr; p.act = a.act;
+  p.col0_bias_only = a.zero_wrow0 ? 1 : 0;
+  p.ntn = cdiv(a.N, bn);
+  const long long ntm = cdiv(a.M, BM);
+  EDGL_REQUIRE(ntm * p.ntn < (1ll << 31), "gemm_tc: too many tiles");
+  p.num_tiles = (int)(ntm * p.ntn);
+  p.kblocks = cdiv(a.K, BK);
+  const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
+  if (bn == 256) {
+    auto kern = gemm_tc_kernel<256>;
+    EDGL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<256>::BYTES));
+    kern<<<grid, NTHREADS, Smem<256>::BYTES, st>>>(mapA, mapB, p);
+  } else {
+    auto kern = gemm_tc_kernel<128>;
+    EDGL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<128>::BYTES));
+    kern<<<grid, NTHREADS, Smem<128>::BYTES, st>>>(mapA, mapB, p);
+  }
+  EDGL_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace edgl

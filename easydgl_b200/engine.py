@@ -299,6 +299,20 @@ def dense(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], act: int 
     return out
 
 
+def dense_nk(x: torch.Tensor, wt: torch.Tensor, b: Optional[torch.Tensor], act: int = 0) -> torch.Tensor:
+    """dense layer with the kernel stored K-major (wt [N,K]): the tcgen05 tensor-core GEMM."""
+    lib = _lib.load()
+    x = _req(x, torch.float32, "x")
+    wt = _req(wt, torch.float32, "wt", x.device)
+    N, K = wt.shape
+    M = x.numel() // K
+    out = torch.empty(tuple(x.shape[:-1]) + (N,), dtype=torch.float32, device=x.device)
+    bb = None if b is None else _req(b, torch.float32, "b", x.device)
+    with torch.cuda.device(x.device):
+        check(lib.edgl_dense_nk(x.data_ptr(), wt.data_ptr(), _ptr(bb), M, K, N, act, out.data_ptr(), _stream()))
+    return out
+
+
 def topk(logits: torch.Tensor, k: int, seen_ids: Optional[torch.Tensor] = None):
     """Sequential.eval ranking on given logits (modified in place when seen_ids is given)."""
     lib = _lib.load()

@@ -150,6 +150,10 @@ int edgl_layernorm(const float* x, const float* gamma, const float* beta, int B,
 /* tf.layers.dense(x, N, activation) (act: 0 none, 1 gelu-erf EasyDGL.py:19-32, 2 relu): x [M,K] @ w [K,N] + b. */
 int edgl_dense(const float* x, const float* w, const float* b, int M, int K, int N, int act, float* out,
                void* stream);
+/* Same layer with the kernel stored K-major, wt [N,K] = w^T (how edgl_commit keeps every dense kernel):
+ * the tcgen05 tensor-core path (3xTF32, fp32-level accuracy). */
+int edgl_dense_nk(const float* x, const float* wt, const float* b, int M, int K, int N, int act, float* out,
+                  void* stream);
 /* Sequential.eval ranking on given logits (Base.py:156-181): logits [B,N] are modified in place
  * (seen ids -> -inf) when seen_ids != NULL. */
 int edgl_topk(float* logits, int B, int N, const int64_t* seen_ids, int seen_len, int K, int32_t* idx,

@@ -108,6 +108,25 @@ def test_dense(M, K, N, act):
     assert_close(out, ref, 1e-5, "dense act=%d" % act)
 
 
+@pytest.mark.parametrize("M,K,N,act", [(128, 32, 128, 0), (5, 32, 16, 0), (130, 64, 128, 1), (257, 144, 512, 0),
+                                       (300, 128, 256, 2), (1000, 256, 128, 1), (77, 128, 18001, 0),
+                                       (40000, 128, 128, 0), (20000, 144, 512, 1)])
+def test_dense_tensor_core(M, K, N, act):
+    """The tcgen05 (3xTF32) GEMM: fp32-level accuracy, M/N/K tails, both tile widths, many tiles per CTA."""
+    from easydgl_b200 import engine
+    g = torch.Generator().manual_seed(40 + M % 7)
+    x = torch.randn(M, K, generator=g)
+    w = torch.randn(K, N, generator=g) / math.sqrt(K)
+    b = torch.randn(N, generator=g)
+    out = engine.dense_nk(x.to(DEV), w.t().contiguous().to(DEV), b.to(DEV), act).cpu()
+    ref = x.double() @ w.double() + b.double()
+    if act == 1:
+        ref = O.gelu(ref)
+    elif act == 2:
+        ref = torch.relu(ref)
+    assert_close(out, ref, 1e-5, "tensor-core dense act=%d" % act)
+
+
 @pytest.mark.parametrize("name", ["easy_a", "easy_b", "easy_c", "ctsma_b"])
 def test_intensity(name):
     """T.MAU.intensity (temporal.py:281-315): G [hB,L,L] and lam [hB,L,E], literal 4-D form as reference."""

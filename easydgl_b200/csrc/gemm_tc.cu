@@ -126,7 +126,7 @@ struct Smem {
   static constexpr int B_BYTES = BN * BK * 4;
   static constexpr int STAGE = 2 * A_BYTES + 2 * B_BYTES;
   static constexpr int STAGES = (BN == 256) ? 2 : 3;
-  static constexpr int BYTES = STAGES * STAGE + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int BYTES = STAGES * STAGE + 1024 /*align*/ + 256 /*barriers*/ + 4 * 32 * 36 * 4 /*epilogue*/;
 };
 
 template <int BN>
@@ -250,54 +250,110 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue
+    // tcgen05.ld hands every thread one accumulator ROW (32 columns).  Writing rows straight to global
+    // would cost 32 cache lines per instruction, so each 32x32 chunk is transposed through a padded
+    // shared-memory tile and then handled 4 rows x 128 B per warp instruction: bias / periodic bias /
+    // residual loads and the output store are all full-line, 16-byte-per-lane accesses.
     const int q = warp & 3;  // TMEM lane quarter this warp may read
-    const bool c_vec = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
-    const bool r_vec = p.R && (p.ldr % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.R) & 15) == 0);
+    float* stg = reinterpret_cast<float*>(base + S * SM::STAGE + 256) + (warp - 4) * (32 * 36);
+    const bool c_al = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+    const bool r_al = p.R && (p.ldr % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.R) & 15) == 0);
+    const bool b_al = p.bias && ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
+    const bool pb_al = p.pbias && (p.N % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.pbias) & 15) == 0);
+    const int cl = (lane & 7) * 4;  // this lane's 4 columns inside a chunk
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tcount) {
       const int acc = tcount & 1;
       const int m0 = (tile / p.ntn) * BM, n0 = (tile % p.ntn) * BN;
       mbar_wait(&tfull[acc], (tcount >> 1) & 1);
       tc_fence_after();
-      const long long row = (long long)m0 + q * 32 + lane;
-      const bool row_ok = row < p.M;
-      const float* pb = (p.pbias && row_ok) ? p.pbias + (row % p.pperiod) * (long long)p.N : nullptr;
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t r[32];
         tmem_ld32(tmem_base + acc * BN + c0 + ((uint32_t)(q * 32) << 16), r);
-        if (!row_ok || n0 + c0 >= p.N) continue;
-        float* crow = p.C + row * p.ldc + n0 + c0;
-        const float* rrow = p.R ? p.R + row * p.ldr + n0 + c0 : nullptr;
+        if (n0 + c0 >= p.N) continue;  // warp-uniform
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const int col = n0 + c0 + j;
-          float v[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float x = __uint_as_float(r[j + e]);
-            const int c = col + e;
-            if (c < p.N) {
-              if (p.col0_bias_only && c == 0) x = 0.f;
-              if (p.bias) x += p.bias[c];
-              if (pb) x += pb[c];
-              if (p.act == ACT_GELU) x = gelu_erf_tc(x);
-              else if (p.act == ACT_RELU) x = fmaxf(x, 0.f);
-            }
-            v[e] = x;
-          }
-          if (col + 3 < p.N && c_vec && (!p.R || r_vec)) {
-            if (rrow) {
-              const float4 rr = *reinterpret_cast<const float4*>(rrow + j);
-              v[0] += rr.x; v[1] += rr.y; v[2] += rr.z; v[3] += rr.w;
-            }
-            *reinterpret_cast<float4*>(crow + j) = make_float4(v[0], v[1], v[2], v[3]);
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(stg + lane * 36 + 4 * j) =
+              make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                          __uint_as_float(r[4 * j + 3]));
+        __syncwarp();
+        const int col = n0 + c0 + cl;
+        const int nval = p.N - col;  // columns of this lane that exist (<=0: none)
+        float bv[4] = {0.f, 0.f, 0.f, 0.f};
+        if (p.bias && nval > 0) {
+          if (b_al && nval >= 4) {
+            const float4 t4 = *reinterpret_cast<const float4*>(p.bias + col);
+            bv[0] = t4.x; bv[1] = t4.y; bv[2] = t4.z; bv[3] = t4.w;
           } else {
 #pragma unroll
             for (int e = 0; e < 4; ++e)
-              if (col + e < p.N) crow[j + e] = v[e] + (rrow ? rrow[j + e] : 0.f);
+              if (e < nval) bv[e] = p.bias[col + e];
           }
         }
+        // issue every global load of the chunk first (8 independent 16-byte loads per operand in flight:
+        // C and R may alias as far as the compiler knows, so an interleaved loop would serialise on DRAM latency)
+        const bool lane_ok = nval > 0;
+        const bool vec4 = nval >= 4;
+        float4 rr[8], pp[8];
+#pragma unroll
+        for (int itr = 0; itr < 8; ++itr) {
+          const int rl = itr * 4 + (lane >> 3);
+          const long long row = (long long)m0 + q * 32 + rl;
+          rr[itr] = make_float4(0.f, 0.f, 0.f, 0.f);
+          pp[itr] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (row < p.M && lane_ok) {
+            if (p.R) {
+              const float* rp = p.R + row * p.ldr + col;
+              if (r_al && vec4) {
+                rr[itr] = *reinterpret_cast<const float4*>(rp);
+              } else {
+                rr[itr].x = rp[0];
+                if (nval > 1) rr[itr].y = rp[1];
+                if (nval > 2) rr[itr].z = rp[2];
+                if (nval > 3) rr[itr].w = rp[3];
+              }
+            }
+            if (p.pbias) {
+              const float* pb = p.pbias + (row % p.pperiod) * (long long)p.N + col;
+              if (pb_al && vec4) {
+                pp[itr] = *reinterpret_cast<const float4*>(pb);
+              } else {
+                pp[itr].x = pb[0];
+                if (nval > 1) pp[itr].y = pb[1];
+                if (nval > 2) pp[itr].z = pb[2];
+                if (nval > 3) pp[itr].w = pb[3];
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int itr = 0; itr < 8; ++itr) {
+          const int rl = itr * 4 + (lane >> 3);
+          const long long row = (long long)m0 + q * 32 + rl;
+          if (row >= p.M || !lane_ok) continue;
+          const float4 a4 = *reinterpret_cast<const float4*>(stg + rl * 36 + cl);
+          float v[4] = {a4.x, a4.y, a4.z, a4.w};
+          if (p.col0_bias_only && col == 0) v[0] = 0.f;
+          const float pv[4] = {pp[itr].x, pp[itr].y, pp[itr].z, pp[itr].w};
+          const float rv[4] = {rr[itr].x, rr[itr].y, rr[itr].z, rr[itr].w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float x = (v[e] + pv[e]) + bv[e];
+            if (p.act == ACT_GELU) x = gelu_erf_tc(x);
+            else if (p.act == ACT_RELU) x = fmaxf(x, 0.f);
+            v[e] = x + rv[e];
+          }
+          float* cp = p.C + row * p.ldc + col;
+          if (c_al && vec4) {
+            *reinterpret_cast<float4*>(cp) = make_float4(v[0], v[1], v[2], v[3]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (e < nval) cp[e] = v[e];
+          }
+        }
+        __syncwarp();
       }
       tc_fence_before();
       mbar_arrive(&tempty[acc]);

@@ -117,7 +117,7 @@ struct Params {
 };
 
 __device__ __forceinline__ float gelu_erf_tc(float x) {
-  return x * (0.5f * (1.0f + erff(__fdiv_rn(x, 1.41421356237309504880f))));  // EasyDGL.py:31-32
+  return x * (0.5f * (1.0f + erff(x * 0.70710678118654752440f)));  // EasyDGL.py:31-32 (x/sqrt(2) as x*(1/sqrt 2): <= 1 ulp)
 }
 
 template <int BN>
@@ -129,7 +129,7 @@ struct Smem {
   static constexpr int BYTES = STAGES * STAGE + 1024 /*align*/ + 256 /*barriers*/ + 4 * 32 * 36 * 4 /*epilogue*/;
 };
 
-template <int BN>
+template <int BN, int ACT>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, Params p) {
   using SM = Smem<BN>;
@@ -253,18 +253,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     // tcgen05.ld hands every thread one accumulator ROW (32 columns).  Writing rows straight to global
     // would cost 32 cache lines per instruction, so each 32x32 chunk is transposed through a padded
     // shared-memory tile and then handled 4 rows x 128 B per warp instruction: bias / periodic bias /
-    // residual loads and the output store are all full-line, 16-byte-per-lane accesses.
+    // residual loads and the output store are all full-line, 16-byte-per-lane accesses, and every load
+    // of a chunk is issued before the first store (C and R may alias as far as the compiler knows).
     const int q = warp & 3;  // TMEM lane quarter this warp may read
     float* stg = reinterpret_cast<float*>(base + S * SM::STAGE + 256) + (warp - 4) * (32 * 36);
-    const bool c_al = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
-    const bool r_al = p.R && (p.ldr % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.R) & 15) == 0);
-    const bool b_al = p.bias && ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
-    const bool pb_al = p.pbias && (p.N % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.pbias) & 15) == 0);
+    const bool all_al = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
+                        (!p.R || ((p.ldr % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.R) & 15) == 0))) &&
+                        (!p.bias || ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0)) &&
+                        (!p.pbias || ((p.N % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.pbias) & 15) == 0)));
     const int cl = (lane & 7) * 4;  // this lane's 4 columns inside a chunk
+    const int rsub = lane >> 3;     // this lane's row inside a group of 4
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tcount) {
       const int acc = tcount & 1;
       const int m0 = (tile / p.ntn) * BM, n0 = (tile % p.ntn) * BN;
+      const int rbase = m0 + q * 32 + rsub;  // rows rbase + 4*itr
+      int pbo[8];                            // periodic-bias row offsets (row % period) * N
+      if (p.pbias) {
+        int pr = rbase % p.pperiod;
+        const int step = 4 % p.pperiod;
+#pragma unroll
+        for (int itr = 0; itr < 8; ++itr) {
+          pbo[itr] = pr * p.N;
+          pr += step;
+          if (pr >= p.pperiod) pr -= p.pperiod;
+        }
+      }
       mbar_wait(&tfull[acc], (tcount >> 1) & 1);
       tc_fence_after();
 #pragma unroll 1
@@ -279,78 +293,54 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                           __uint_as_float(r[4 * j + 3]));
         __syncwarp();
         const int col = n0 + c0 + cl;
-        const int nval = p.N - col;  // columns of this lane that exist (<=0: none)
-        float bv[4] = {0.f, 0.f, 0.f, 0.f};
-        if (p.bias && nval > 0) {
-          if (b_al && nval >= 4) {
-            const float4 t4 = *reinterpret_cast<const float4*>(p.bias + col);
-            bv[0] = t4.x; bv[1] = t4.y; bv[2] = t4.z; bv[3] = t4.w;
-          } else {
+        if (all_al && n0 + c0 + 32 <= p.N) {
+          // ---- fast path: whole chunk inside N, everything 16-byte aligned
+          float4 rr[8], pp[8];
+          if (p.R) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e)
-              if (e < nval) bv[e] = p.bias[col + e];
-          }
-        }
-        // issue every global load of the chunk first (8 independent 16-byte loads per operand in flight:
-        // C and R may alias as far as the compiler knows, so an interleaved loop would serialise on DRAM latency)
-        const bool lane_ok = nval > 0;
-        const bool vec4 = nval >= 4;
-        float4 rr[8], pp[8];
-#pragma unroll
-        for (int itr = 0; itr < 8; ++itr) {
-          const int rl = itr * 4 + (lane >> 3);
-          const long long row = (long long)m0 + q * 32 + rl;
-          rr[itr] = make_float4(0.f, 0.f, 0.f, 0.f);
-          pp[itr] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (row < p.M && lane_ok) {
-            if (p.R) {
-              const float* rp = p.R + row * p.ldr + col;
-              if (r_al && vec4) {
-                rr[itr] = *reinterpret_cast<const float4*>(rp);
-              } else {
-                rr[itr].x = rp[0];
-                if (nval > 1) rr[itr].y = rp[1];
-                if (nval > 2) rr[itr].z = rp[2];
-                if (nval > 3) rr[itr].w = rp[3];
-              }
-            }
-            if (p.pbias) {
-              const float* pb = p.pbias + (row % p.pperiod) * (long long)p.N + col;
-              if (pb_al && vec4) {
-                pp[itr] = *reinterpret_cast<const float4*>(pb);
-              } else {
-                pp[itr].x = pb[0];
-                if (nval > 1) pp[itr].y = pb[1];
-                if (nval > 2) pp[itr].z = pb[2];
-                if (nval > 3) pp[itr].w = pb[3];
-              }
+            for (int itr = 0; itr < 8; ++itr) {
+              const int row = rbase + 4 * itr;
+              rr[itr] = row < p.M ? *reinterpret_cast<const float4*>(p.R + (size_t)row * p.ldr + col)
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
             }
           }
-        }
+          if (p.pbias) {
 #pragma unroll
-        for (int itr = 0; itr < 8; ++itr) {
-          const int rl = itr * 4 + (lane >> 3);
-          const long long row = (long long)m0 + q * 32 + rl;
-          if (row >= p.M || !lane_ok) continue;
-          const float4 a4 = *reinterpret_cast<const float4*>(stg + rl * 36 + cl);
-          float v[4] = {a4.x, a4.y, a4.z, a4.w};
-          if (p.col0_bias_only && col == 0) v[0] = 0.f;
-          const float pv[4] = {pp[itr].x, pp[itr].y, pp[itr].z, pp[itr].w};
-          const float rv[4] = {rr[itr].x, rr[itr].y, rr[itr].z, rr[itr].w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float x = (v[e] + pv[e]) + bv[e];
-            if (p.act == ACT_GELU) x = gelu_erf_tc(x);
-            else if (p.act == ACT_RELU) x = fmaxf(x, 0.f);
-            v[e] = x + rv[e];
+            for (int itr = 0; itr < 8; ++itr) pp[itr] = *reinterpret_cast<const float4*>(p.pbias + pbo[itr] + col);
           }
-          float* cp = p.C + row * p.ldc + col;
-          if (c_al && vec4) {
-            *reinterpret_cast<float4*>(cp) = make_float4(v[0], v[1], v[2], v[3]);
-          } else {
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.bias) b4 = *reinterpret_cast<const float4*>(p.bias + col);
 #pragma unroll
-            for (int e = 0; e < 4; ++e)
-              if (e < nval) cp[e] = v[e];
+          for (int itr = 0; itr < 8; ++itr) {
+            const int row = rbase + 4 * itr;
+            float4 v = *reinterpret_cast<const float4*>(stg + (rsub + 4 * itr) * 36 + cl);
+            if (p.col0_bias_only && col == 0) v.x = 0.f;
+            if (p.pbias) { v.x += pp[itr].x; v.y += pp[itr].y; v.z += pp[itr].z; v.w += pp[itr].w; }
+            v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
+            if (ACT == ACT_GELU) { v.x = gelu_erf_tc(v.x); v.y = gelu_erf_tc(v.y); v.z = gelu_erf_tc(v.z); v.w = gelu_erf_tc(v.w); }
+            if (ACT == ACT_RELU) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+            if (p.R) { v.x += rr[itr].x; v.y += rr[itr].y; v.z += rr[itr].z; v.w += rr[itr].w; }
+            if (row < p.M) *reinterpret_cast<float4*>(p.C + (size_t)row * p.ldc + col) = v;
+          }
+        } else {
+          // ---- generic path (N tail / unaligned operands): scalar, guarded
+#pragma unroll 1
+          for (int itr = 0; itr < 8; ++itr) {
+            const int row = rbase + 4 * itr;
+            if (row >= p.M) continue;
+#pragma unroll 1
+            for (int e = 0; e < 4; ++e) {
+              const int c = col + e;
+              if (c >= p.N) continue;
+              float x = stg[(rsub + 4 * itr) * 36 + cl + e];
+              if (p.col0_bias_only && c == 0) x = 0.f;
+              if (p.pbias) x += p.pbias[(size_t)(row % p.pperiod) * p.N + c];
+              if (p.bias) x += p.bias[c];
+              if (ACT == ACT_GELU) x = gelu_erf_tc(x);
+              if (ACT == ACT_RELU) x = fmaxf(x, 0.f);
+              if (p.R) x += p.R[(size_t)row * p.ldr + c];
+              p.C[(size_t)row * p.ldc + c] = x;
+            }
           }
         }
         __syncwarp();
@@ -433,15 +423,22 @@ int launch_gemm_tc(const GemmArgs& a, cudaStream_t st) {
   p.num_tiles = (int)(ntm * p.ntn);
   p.kblocks = cdiv(a.K, BK);
   const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
-  if (bn == 256) {
-    auto kern = gemm_tc_kernel<256>;
-    EDGL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<256>::BYTES));
-    kern<<<grid, NTHREADS, Smem<256>::BYTES, st>>>(mapA, mapB, p);
-  } else {
-    auto kern = gemm_tc_kernel<128>;
-    EDGL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<128>::BYTES));
-    kern<<<grid, NTHREADS, Smem<128>::BYTES, st>>>(mapA, mapB, p);
+#define EDGL_TC_LAUNCH(BNV, ACTV)                                                                              \
+  {                                                                                                            \
+    auto kern = gemm_tc_kernel<BNV, ACTV>;                                                                     \
+    EDGL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BNV>::BYTES));      \
+    kern<<<grid, NTHREADS, Smem<BNV>::BYTES, st>>>(mapA, mapB, p);                                             \
   }
+  if (bn == 256) {
+    if (a.act == ACT_GELU) EDGL_TC_LAUNCH(256, ACT_GELU)
+    else if (a.act == ACT_RELU) EDGL_TC_LAUNCH(256, ACT_RELU)
+    else EDGL_TC_LAUNCH(256, ACT_NONE)
+  } else {
+    if (a.act == ACT_GELU) EDGL_TC_LAUNCH(128, ACT_GELU)
+    else if (a.act == ACT_RELU) EDGL_TC_LAUNCH(128, ACT_RELU)
+    else EDGL_TC_LAUNCH(128, ACT_NONE)
+  }
+#undef EDGL_TC_LAUNCH
   EDGL_LAUNCH_CHECK();
   return 0;
 }

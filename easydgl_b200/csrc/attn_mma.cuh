@@ -47,6 +47,12 @@ __device__ __forceinline__ void split4(const float (&x)[4], uint32_t (&h)[4], ui
   }
 }
 
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -63,6 +69,56 @@ struct AttnMmaLayout {
     return (size_t)3 * LP * SK + (size_t)LP * SE + (size_t)DH * SW + 3 * NC + E + LP;
   }
 };
+
+// out[KS][4] = P[NT][.] (accumulator layout, keys permuted) times X (shared [LP][DH+4]).
+// Two key tiles and all DH/8 output tiles are issued interleaved per split term; even / odd key tiles
+// accumulate into separate registers, so every accumulator is touched once per 2*KS MMAs.
+template <int DH, int NT>
+__device__ __forceinline__ void pv_product(const float (&P)[NT][4], const float* Xs, float (&out)[DH / 8][4], int g,
+                                           int t) {
+  constexpr int KS = DH / 8, SK = DH + 4;
+  float acc[2][KS][4];
+#pragma unroll
+  for (int p = 0; p < 2; ++p)
+#pragma unroll
+    for (int n = 0; n < KS; ++n) acc[p][n][0] = acc[p][n][1] = acc[p][n][2] = acc[p][n][3] = 0.f;
+#pragma unroll
+  for (int nt0 = 0; nt0 < NT; nt0 += 2) {
+    uint32_t ph[2][4], pl[2][4];
+    float b0[2][KS], b1[2][KS];
+#pragma unroll
+    for (int p = 0; p < 2; ++p)
+      if (nt0 + p < NT) {
+        const float pa[4] = {P[nt0 + p][0], P[nt0 + p][2], P[nt0 + p][1], P[nt0 + p][3]};
+        split4(pa, ph[p], pl[p]);
+#pragma unroll
+        for (int n = 0; n < KS; ++n) {
+          const float* xp = Xs + ((nt0 + p) * 8 + 2 * t) * SK + n * 8 + g;
+          b0[p][n] = xp[0];
+          b1[p][n] = xp[SK];
+        }
+      }
+#pragma unroll
+    for (int p = 0; p < 2; ++p)
+      if (nt0 + p < NT)
+#pragma unroll
+        for (int n = 0; n < KS; ++n) mma_tf32(acc[p][n], pl[p], __float_as_uint(b0[p][n]), __float_as_uint(b1[p][n]));
+#pragma unroll
+    for (int p = 0; p < 2; ++p)
+      if (nt0 + p < NT)
+#pragma unroll
+        for (int n = 0; n < KS; ++n) mma_tf32(acc[p][n], ph[p], tf32_lo(b0[p][n]), tf32_lo(b1[p][n]));
+#pragma unroll
+    for (int p = 0; p < 2; ++p)
+      if (nt0 + p < NT)
+#pragma unroll
+        for (int n = 0; n < KS; ++n) mma_tf32(acc[p][n], ph[p], __float_as_uint(b0[p][n]), __float_as_uint(b1[p][n]));
+  }
+#pragma unroll
+  for (int n = 0; n < KS; ++n)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) out[n][c] = acc[0][n][c] + acc[1][n][c];
+}
 
 // NT = number of 8-key tiles held in registers (L <= 8*NT)
 template <int DH, int E, int NT>
@@ -110,10 +166,12 @@ __global__ void __launch_bounds__(256, (NT <= 16) ? 2 : 1) attention_mma_kernel(
     Ms[k * SE + e] = (k < L) ? (float)a.marks[(row0 + k) * E + e] : 0.f;
   }
   for (int i = tid; i < LP; i += nthr) km[i] = (i < L) ? (a.kmask[row0 + i] ? 1.f : 0.f) : -1.f;
-  for (int i = tid; i < DH * NC; i += nthr) W1[(i / NC) * SW + (i % NC)] = a.int_w[i];
+  // The MLP operands are staged pre-multiplied by -log2(e): the MMA then yields -z*log2(e) directly and
+  // sigmoid(z) = 1 / (1 + 2^(-z log2 e)) costs one ex2, one add, one rcp (tf.nn.sigmoid, temporal.py:290).
+  for (int i = tid; i < DH * NC; i += nthr) W1[(i / NC) * SW + (i % NC)] = -kLog2e * a.int_w[i];
   for (int i = tid; i < NC; i += nthr) {
-    wsp[i] = a.int_w[DH * NC + i];
-    b1[i] = a.int_b[i];
+    wsp[i] = -kLog2e * a.int_w[DH * NC + i];
+    b1[i] = -kLog2e * a.int_b[i];
     wv[i] = a.int_weight[i];
   }
   for (int i = tid; i < E; i += nthr) sc[i] = expf(a.int_scaling[i]);  // temporal.py:302
@@ -137,27 +195,49 @@ __global__ void __launch_bounds__(256, (NT <= 16) ? 2 : 1) attention_mma_kernel(
       x[3] = a.Q[rb * a.ldq + hh * DH + ks * 8 + t + 4];
       split4(x, qh[ks], ql[ks]);
     }
-    // ---- S = Q K^T  (accumulators P[nt][c]: rows g / g+8, keys nt*8 + 2t + (c&1))
+    // ---- S = Q K^T  (accumulators P[nt][c]: rows g / g+8, keys nt*8 + 2t + (c&1)).
+    // Four key tiles are in flight at a time and the three split terms are issued tile-interleaved, so
+    // consecutive MMAs never touch the same accumulator (tensor-pipe latency hidden inside one warp).
     float P[NT][4];
 #pragma unroll
-    for (int nt = 0; nt < NT; ++nt) {
-      P[nt][0] = P[nt][1] = P[nt][2] = P[nt][3] = 0.f;
+    for (int nt = 0; nt < NT; ++nt) P[nt][0] = P[nt][1] = P[nt][2] = P[nt][3] = 0.f;
+#pragma unroll
+    for (int n0 = 0; n0 < NT; n0 += 4) {
 #pragma unroll
       for (int ks = 0; ks < KS; ++ks) {
-        const float* kp = Ks + (nt * 8 + g) * SK + ks * 8 + t;
-        mma3(P[nt], qh[ks], ql[ks], kp[0], kp[4]);
+        float b0[4], b1[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (n0 + j < NT) {
+            const float* kp = Ks + ((n0 + j) * 8 + g) * SK + ks * 8 + t;
+            b0[j] = kp[0];
+            b1[j] = kp[4];
+          }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (n0 + j < NT) mma_tf32(P[n0 + j], ql[ks], __float_as_uint(b0[j]), __float_as_uint(b1[j]));
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (n0 + j < NT) mma_tf32(P[n0 + j], qh[ks], tf32_lo(b0[j]), tf32_lo(b1[j]));
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (n0 + j < NT) mma_tf32(P[n0 + j], qh[ks], __float_as_uint(b0[j]), __float_as_uint(b1[j]));
       }
     }
-    // ---- scale, key mask, causal mask, softmax (rows live in a quad: 2 shuffles per reduction)
+    // ---- scale, key mask, causal mask, softmax (rows live in a quad: 2 shuffles per reduction).
+    // Scores are kept in the log2 domain: s' = S * (log2(e)/sqrt(dh)); the masked fill is any huge
+    // negative constant (all-masked rows must come out uniform, Q8), columns beyond L are -inf.
+    const float sc2 = inv_sqrt_dh * kLog2e;
     float ma = -INFINITY, mb = -INFINITY;
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
+      const float k0 = km[nt * 8 + 2 * t], k1 = km[nt * 8 + 2 * t + 1];
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         const int col = nt * 8 + 2 * t + (c & 1);
         const int qr = (c < 2) ? qa : qb;
-        const float kmv = km[col];
-        float s = P[nt][c] * inv_sqrt_dh;
+        const float kmv = (c & 1) ? k1 : k0;
+        float s = P[nt][c] * sc2;
         if (kmv == 0.f || (a.causal && col > qr)) s = kFillMma;
         if (kmv < 0.f) s = -INFINITY;  // beyond L: not a key at all
         P[nt][c] = s;
@@ -173,8 +253,7 @@ __global__ void __launch_bounds__(256, (NT <= 16) ? 2 : 1) attention_mma_kernel(
     for (int nt = 0; nt < NT; ++nt) {
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        const float m = (c < 2) ? ma : mb;
-        const float p = ex2_approx((P[nt][c] - m) * kLog2e);
+        const float p = ex2_approx(P[nt][c] - ((c < 2) ? ma : mb));
         P[nt][c] = p;
         if (c < 2) la += p; else lb += p;
       }
@@ -190,19 +269,7 @@ __global__ void __launch_bounds__(256, (NT <= 16) ? 2 : 1) attention_mma_kernel(
     }
     // ---- H = P T   (k = keys, permuted: slot t <-> key 2t, slot t+4 <-> key 2t+1)
     float H[KS][4];
-#pragma unroll
-    for (int n = 0; n < KS; ++n) H[n][0] = H[n][1] = H[n][2] = H[n][3] = 0.f;
-#pragma unroll
-    for (int nt = 0; nt < NT; ++nt) {
-      const float pa[4] = {P[nt][0], P[nt][2], P[nt][1], P[nt][3]};
-      uint32_t ph[4], pl[4];
-      split4(pa, ph, pl);
-#pragma unroll
-      for (int n = 0; n < KS; ++n) {
-        const float* tp = Ts + (nt * 8 + 2 * t) * SK + n * 8 + g;
-        mma3(H[n], ph, pl, tp[0], tp[SK]);
-      }
-    }
+    pv_product<DH, NT>(P, Ts, H, g, t);
     // ---- intensity MLP: Z = sigmoid([H, span] W1 + b1); dot with w per event (temporal.py:287-305)
     const float spa = a.spans[ra], spb = a.spans[rb];
     uint32_t hh_[KS][4], hl_[KS][4];
@@ -212,36 +279,62 @@ __global__ void __launch_bounds__(256, (NT <= 16) ? 2 : 1) attention_mma_kernel(
       split4(ha, hh_[ks], hl_[ks]);
     }
     float lsa[E], lsb[E];  // per-event dot products for rows qa / qb (full sums after the quad reduce)
-#pragma unroll
-    for (int e = 0; e < E; ++e) {
+    {
+      constexpr int MT = E * KS;  // 8-column tiles of the MLP output; tile tt belongs to event tt / KS
       float pa = 0.f, pb = 0.f;
 #pragma unroll
-      for (int jj = 0; jj < KS; ++jj) {
-        const int n0 = (e * KS + jj) * 8;
-        float z[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int tg = 0; tg < MT; tg += 4) {
+        float z[4][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) z[j][0] = z[j][1] = z[j][2] = z[j][3] = 0.f;
 #pragma unroll
         for (int ks = 0; ks < KS; ++ks) {
-          const float* wp = W1 + (ks * 8 + 2 * t) * SW + n0 + g;
-          mma3(z, hh_[ks], hl_[ks], wp[0], wp[SW]);
+          float b0[4], b1[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (tg + j < MT) {
+              const float* wp = W1 + (ks * 8 + 2 * t) * SW + (tg + j) * 8 + g;
+              b0[j] = wp[0];
+              b1[j] = wp[SW];
+            }
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (tg + j < MT) mma_tf32(z[j], hl_[ks], __float_as_uint(b0[j]), __float_as_uint(b1[j]));
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (tg + j < MT) mma_tf32(z[j], hh_[ks], tf32_lo(b0[j]), tf32_lo(b1[j]));
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (tg + j < MT) mma_tf32(z[j], hh_[ks], __float_as_uint(b0[j]), __float_as_uint(b1[j]));
         }
-        const int c0 = n0 + 2 * t;
-        const float2 bb = *reinterpret_cast<const float2*>(b1 + c0);
-        const float2 ws = *reinterpret_cast<const float2*>(wsp + c0);
-        const float2 we = *reinterpret_cast<const float2*>(wv + c0);
-        const float z0 = z[0] + fmaf(spa, ws.x, bb.x), z1 = z[1] + fmaf(spa, ws.y, bb.y);
-        const float z2 = z[2] + fmaf(spb, ws.x, bb.x), z3 = z[3] + fmaf(spb, ws.y, bb.y);
-        // sigmoid = 1 / (1 + 2^(-z log2 e))
-        pa = fmaf(__frcp_rn(1.f + ex2_approx(-z0 * kLog2e)), we.x, pa);
-        pa = fmaf(__frcp_rn(1.f + ex2_approx(-z1 * kLog2e)), we.y, pa);
-        pb = fmaf(__frcp_rn(1.f + ex2_approx(-z2 * kLog2e)), we.x, pb);
-        pb = fmaf(__frcp_rn(1.f + ex2_approx(-z3 * kLog2e)), we.y, pb);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (tg + j < MT) {
+            const int tt = tg + j;
+            const int c0 = tt * 8 + 2 * t;
+            const float2 bb = *reinterpret_cast<const float2*>(b1 + c0);
+            const float2 ws = *reinterpret_cast<const float2*>(wsp + c0);
+            const float2 we = *reinterpret_cast<const float2*>(wv + c0);
+            const float z0 = z[j][0] + fmaf(spa, ws.x, bb.x), z1 = z[j][1] + fmaf(spa, ws.y, bb.y);
+            const float z2 = z[j][2] + fmaf(spb, ws.x, bb.x), z3 = z[j][3] + fmaf(spb, ws.y, bb.y);
+            // z* already hold -z*log2(e): sigmoid = 1 / (1 + 2^(z*))
+            pa = fmaf(rcp_approx(1.f + ex2_approx(z0)), we.x, pa);
+            pa = fmaf(rcp_approx(1.f + ex2_approx(z1)), we.y, pa);
+            pb = fmaf(rcp_approx(1.f + ex2_approx(z2)), we.x, pb);
+            pb = fmaf(rcp_approx(1.f + ex2_approx(z3)), we.y, pb);
+            if ((tt % KS) == KS - 1) {  // event complete: reduce over the quad (columns live across lanes t)
+              pa += __shfl_xor_sync(0xffffffffu, pa, 1);
+              pa += __shfl_xor_sync(0xffffffffu, pa, 2);
+              pb += __shfl_xor_sync(0xffffffffu, pb, 1);
+              pb += __shfl_xor_sync(0xffffffffu, pb, 2);
+              lsa[tt / KS] = pa;
+              lsb[tt / KS] = pb;
+              pa = 0.f;
+              pb = 0.f;
+            }
+          }
+        }
       }
-      pa += __shfl_xor_sync(0xffffffffu, pa, 1);
-      pa += __shfl_xor_sync(0xffffffffu, pa, 2);
-      pb += __shfl_xor_sync(0xffffffffu, pb, 1);
-      pb += __shfl_xor_sync(0xffffffffu, pb, 2);
-      lsa[e] = pa;
-      lsb[e] = pb;
     }
     // ---- lam_e = s_e log(1 + exp(x / s_e))  (temporal.py:305-306); lane t owns events t, t+4, t+8, ...
     uint32_t lh[ES][4], ll[ES][4];
@@ -269,38 +362,42 @@ __global__ void __launch_bounds__(256, (NT <= 16) ? 2 : 1) attention_mma_kernel(
     }
     // ---- G = lam M^T (marks exact in TF32: 2 MMAs), set_diag, gate: P <- G o P   (temporal.py:309-313,438-441)
 #pragma unroll
-    for (int nt = 0; nt < NT; ++nt) {
-      float G[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int n0 = 0; n0 < NT; n0 += 4) {
+      float G[4][4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) G[j][0] = G[j][1] = G[j][2] = G[j][3] = 0.f;
 #pragma unroll
       for (int ks = 0; ks < ES; ++ks) {
-        const float* mp = Ms + (nt * 8 + g) * SE + ks * 8 + t;
-        const uint32_t m0 = __float_as_uint(mp[0]), m1 = __float_as_uint(mp[4]);
-        mma_tf32(G, ll[ks], m0, m1);
-        mma_tf32(G, lh[ks], m0, m1);
+        uint32_t m0[4], m1[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (n0 + j < NT) {
+            const float* mp = Ms + ((n0 + j) * 8 + g) * SE + ks * 8 + t;
+            m0[j] = __float_as_uint(mp[0]);
+            m1[j] = __float_as_uint(mp[4]);
+          }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (n0 + j < NT) mma_tf32(G[j], ll[ks], m0[j], m1[j]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (n0 + j < NT) mma_tf32(G[j], lh[ks], m0[j], m1[j]);
       }
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const int col = nt * 8 + 2 * t + (c & 1);
-        const int qr = (c < 2) ? qa : qb;
-        const float gg = (a.diag_one && col == qr) ? 1.f : G[c];
-        P[nt][c] *= gg;
-      }
+      for (int j = 0; j < 4; ++j)
+        if (n0 + j < NT) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int col = (n0 + j) * 8 + 2 * t + (c & 1);
+            const int qr = (c < 2) ? qa : qb;
+            const float gg = (a.diag_one && col == qr) ? 1.f : G[j][c];
+            P[n0 + j][c] *= gg;
+          }
+        }
     }
     // ---- O = (G o P) V
     float O[KS][4];
-#pragma unroll
-    for (int n = 0; n < KS; ++n) O[n][0] = O[n][1] = O[n][2] = O[n][3] = 0.f;
-#pragma unroll
-    for (int nt = 0; nt < NT; ++nt) {
-      const float pa[4] = {P[nt][0], P[nt][2], P[nt][1], P[nt][3]};
-      uint32_t ph[4], pl[4];
-      split4(pa, ph, pl);
-#pragma unroll
-      for (int n = 0; n < KS; ++n) {
-        const float* vp = Vs + (nt * 8 + 2 * t) * SK + n * 8 + g;
-        mma3(O[n], ph, pl, vp[0], vp[SK]);
-      }
-    }
+    pv_product<DH, NT>(P, Vs, O, g, t);
     // ---- residual + store (temporal.py:385,447)
 #pragma unroll
     for (int n = 0; n < KS; ++n) {

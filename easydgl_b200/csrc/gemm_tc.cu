@@ -9,10 +9,10 @@
 // over the freshly landed TMA tiles - the swizzled layout is preserved because the op is element-wise),
 // so HBM/L2 only ever carry the fp32 operands once.
 //
-// Roles (384 threads, 1 CTA/SM, persistent over 128 x BN output tiles):
-//   warp 0      TMA producer            warp 1      tcgen05.mma issuer (one elected lane)
-//   warp 2      TMEM allocator          warps 4-7   epilogue: tcgen05.ld -> bias/act/residual -> global
-//   warps 8-11  splitters (A_lo, W_lo)
+// Roles (512 threads, 1 CTA/SM, persistent over 128 x BN output tiles):
+//   warp 0        TMA producer            warp 1       tcgen05.mma issuer (one elected lane)
+//   warp 2        TMEM allocator          warps 4-11   epilogue: tcgen05.ld -> bias/act/residual -> global
+//   warps 12-15   splitters (A_lo, W_lo)               (two epilogue warps per TMEM lane quarter)
 // Pipelines: full[s] (TMA landed) -> split[s] (lo halves written) -> MMA -> empty[s];
 //            tmem_full[a] (tile accumulated) -> epilogue -> tmem_empty[a]  (two TMEM accumulators).
 #include <cuda.h>
@@ -26,7 +26,9 @@ namespace tc {
 constexpr int BM = 128;      // UMMA M
 constexpr int BK = 32;       // floats per k-block = one 128-byte swizzle row
 constexpr int UK = 8;        // UMMA K for tf32 (32 bytes)
-constexpr int NTHREADS = 384;
+constexpr int NTHREADS = 512;
+constexpr int CW = 16;       // epilogue sub-chunk width (columns per tcgen05.ld)
+constexpr int CP = CW + 4;   // padded pitch of the epilogue staging tile
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -105,6 +107,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 struct Params {
   float* C; int ldc;
   int M, N, K;
@@ -126,7 +138,7 @@ struct Smem {
   static constexpr int B_BYTES = BN * BK * 4;
   static constexpr int STAGE = 2 * A_BYTES + 2 * B_BYTES;
   static constexpr int STAGES = (BN == 256) ? 2 : 3;
-  static constexpr int BYTES = STAGES * STAGE + 1024 /*align*/ + 256 /*barriers*/ + 4 * 32 * 36 * 4 /*epilogue*/;
+  static constexpr int BYTES = STAGES * STAGE + 1024 /*align*/ + 256 /*barriers*/ + 8 * 32 * CP * 4 /*epilogue*/;
 };
 
 template <int BN, int ACT>
@@ -158,7 +170,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 128);
+      mbar_init(&tempty[i], 256);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -220,9 +232,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         umma_commit(&tfull[acc]);          // accumulator complete
       }
     }
-  } else if (warp >= 8) {
+  } else if (warp >= 12) {
     // ------------------------------------------------------------------ splitters: lo = x - tf32(x)
-    const int t = threadIdx.x - 256;  // 0..127
+    const int t = threadIdx.x - 384;  // 0..127
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       for (int kb = 0; kb < KB; ++kb, ++it) {
@@ -255,25 +267,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     // shared-memory tile and then handled 4 rows x 128 B per warp instruction: bias / periodic bias /
     // residual loads and the output store are all full-line, 16-byte-per-lane accesses, and every load
     // of a chunk is issued before the first store (C and R may alias as far as the compiler knows).
-    const int q = warp & 3;  // TMEM lane quarter this warp may read
-    float* stg = reinterpret_cast<float*>(base + S * SM::STAGE + 256) + (warp - 4) * (32 * 36);
+    const int q = warp & 3;            // TMEM lane quarter this warp may read
+    const int half = (warp - 4) >> 2;  // the two warps of a quarter take alternate 16-column sub-chunks
+    float* stg = reinterpret_cast<float*>(base + S * SM::STAGE + 256) + (warp - 4) * (32 * CP);
     const bool all_al = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
                         (!p.R || ((p.ldr % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.R) & 15) == 0))) &&
                         (!p.bias || ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0)) &&
                         (!p.pbias || ((p.N % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.pbias) & 15) == 0)));
-    const int cl = (lane & 7) * 4;  // this lane's 4 columns inside a chunk
-    const int rsub = lane >> 3;     // this lane's row inside a group of 4
+    constexpr int LPR = CW / 4;        // lanes per row (4)
+    constexpr int RPI = 32 / LPR;      // rows per warp instruction (8)
+    constexpr int NIT = 32 / RPI;      // iterations per sub-chunk (4)
+    const int cl = (lane % LPR) * 4;   // this lane's 4 columns inside a sub-chunk
+    const int rsub = lane / LPR;       // this lane's row inside a group of RPI
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tcount) {
       const int acc = tcount & 1;
       const int m0 = (tile / p.ntn) * BM, n0 = (tile % p.ntn) * BN;
-      const int rbase = m0 + q * 32 + rsub;  // rows rbase + 4*itr
-      int pbo[8];                            // periodic-bias row offsets (row % period) * N
+      const int rbase = m0 + q * 32 + rsub;  // rows rbase + RPI*itr
+      int pbo[NIT];                          // periodic-bias row offsets (row % period) * N
       if (p.pbias) {
         int pr = rbase % p.pperiod;
-        const int step = 4 % p.pperiod;
+        const int step = RPI % p.pperiod;
 #pragma unroll
-        for (int itr = 0; itr < 8; ++itr) {
+        for (int itr = 0; itr < NIT; ++itr) {
           pbo[itr] = pr * p.N;
           pr += step;
           if (pr >= p.pperiod) pr -= p.pperiod;
@@ -282,38 +298,38 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       mbar_wait(&tfull[acc], (tcount >> 1) & 1);
       tc_fence_after();
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(tmem_base + acc * BN + c0 + ((uint32_t)(q * 32) << 16), r);
+      for (int c0 = half * CW; c0 < BN; c0 += 2 * CW) {
+        uint32_t r[CW];
+        tmem_ld16(tmem_base + acc * BN + c0 + ((uint32_t)(q * 32) << 16), r);
         if (n0 + c0 >= p.N) continue;  // warp-uniform
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<float4*>(stg + lane * 36 + 4 * j) =
+        for (int j = 0; j < CW / 4; ++j)
+          *reinterpret_cast<float4*>(stg + lane * CP + 4 * j) =
               make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
                           __uint_as_float(r[4 * j + 3]));
         __syncwarp();
         const int col = n0 + c0 + cl;
-        if (all_al && n0 + c0 + 32 <= p.N) {
-          // ---- fast path: whole chunk inside N, everything 16-byte aligned
-          float4 rr[8], pp[8];
+        if (all_al && n0 + c0 + CW <= p.N) {
+          // ---- fast path: whole sub-chunk inside N, everything 16-byte aligned
+          float4 rr[NIT], pp[NIT];
           if (p.R) {
 #pragma unroll
-            for (int itr = 0; itr < 8; ++itr) {
-              const int row = rbase + 4 * itr;
+            for (int itr = 0; itr < NIT; ++itr) {
+              const int row = rbase + RPI * itr;
               rr[itr] = row < p.M ? *reinterpret_cast<const float4*>(p.R + (size_t)row * p.ldr + col)
                                   : make_float4(0.f, 0.f, 0.f, 0.f);
             }
           }
           if (p.pbias) {
 #pragma unroll
-            for (int itr = 0; itr < 8; ++itr) pp[itr] = *reinterpret_cast<const float4*>(p.pbias + pbo[itr] + col);
+            for (int itr = 0; itr < NIT; ++itr) pp[itr] = *reinterpret_cast<const float4*>(p.pbias + pbo[itr] + col);
           }
           float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
           if (p.bias) b4 = *reinterpret_cast<const float4*>(p.bias + col);
 #pragma unroll
-          for (int itr = 0; itr < 8; ++itr) {
-            const int row = rbase + 4 * itr;
-            float4 v = *reinterpret_cast<const float4*>(stg + (rsub + 4 * itr) * 36 + cl);
+          for (int itr = 0; itr < NIT; ++itr) {
+            const int row = rbase + RPI * itr;
+            float4 v = *reinterpret_cast<const float4*>(stg + (rsub + RPI * itr) * CP + cl);
             if (p.col0_bias_only && col == 0) v.x = 0.f;
             if (p.pbias) { v.x += pp[itr].x; v.y += pp[itr].y; v.z += pp[itr].z; v.w += pp[itr].w; }
             v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
@@ -325,14 +341,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         } else {
           // ---- generic path (N tail / unaligned operands): scalar, guarded
 #pragma unroll 1
-          for (int itr = 0; itr < 8; ++itr) {
-            const int row = rbase + 4 * itr;
+          for (int itr = 0; itr < NIT; ++itr) {
+            const int row = rbase + RPI * itr;
             if (row >= p.M) continue;
 #pragma unroll 1
             for (int e = 0; e < 4; ++e) {
               const int c = col + e;
               if (c >= p.N) continue;
-              float x = stg[(rsub + 4 * itr) * 36 + cl + e];
+              float x = stg[(rsub + RPI * itr) * CP + cl + e];
               if (p.col0_bias_only && c == 0) x = 0.f;
               if (p.pbias) x += p.pbias[(size_t)(row % p.pperiod) * p.N + c];
               if (p.bias) x += p.bias[c];

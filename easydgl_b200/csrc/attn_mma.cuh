@@ -53,30 +53,61 @@ __device__ __forceinline__ float rcp_approx(float x) {
   return y;
 }
 
+__device__ __forceinline__ float lg2_approx(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
 
+// Shared-memory layout.  B operands (K, V, T, W1) are stored PRE-SPLIT as (hi, lo) pairs when they fit
+// (PS = 2): one 8-byte load then yields both halves and the per-use LOP3+FADD split disappears.
+// Row strides are chosen so that every fragment load is bank-conflict free:
+//   K  : pattern (key g, dim t)      -> stride = 4 (mod 8) elements
+//   V,T: pattern (key 2t, dim g)     -> stride = 2 (mod 8) elements when pre-split, 4 (mod 8) otherwise
+//   W1 : pattern (row 2t, column g)  -> same rule as V/T
 template <int DH, int E>
 struct AttnMmaLayout {
-  static constexpr int SK = DH + 4;       // K/V/T row stride (floats): conflict-free fragment loads
-  static constexpr int SE = E + 4;        // marks row stride
   static constexpr int NC = DH * E;       // intensity MLP width
-  static constexpr int SW = NC + 4;       // W1 row stride (== 4 mod 32)
+  static constexpr bool PRE = (DH <= 16); // pre-split operands fit in shared memory
+  static constexpr int PS = PRE ? 2 : 1;  // floats per element
+  static constexpr int SK = DH + 4;       // K row stride (elements)
+  static constexpr int SV = PRE ? DH + 2 : DH + 4;   // V/T row stride (elements)
+  static constexpr int SE = E + 4;        // marks row stride (floats, never split: small integers are exact)
+  static constexpr int SW = PRE ? NC + 2 : NC + 4;   // W1 row stride (elements)
   __host__ __device__ static size_t floats(int LP) {
-    return (size_t)3 * LP * SK + (size_t)LP * SE + (size_t)DH * SW + 3 * NC + E + LP;
+    return (size_t)PS * ((size_t)LP * SK + 2 * (size_t)LP * SV + (size_t)DH * SW) + (size_t)LP * SE + 3 * NC + E + LP;
   }
 };
 
-// out[KS][4] = P[NT][.] (accumulator layout, keys permuted) times X (shared [LP][DH+4]).
+// B-fragment element: hi = raw fp32 bits (the tensor core reads the top 19), lo = x - tf32(x)
+template <bool PRE>
+__device__ __forceinline__ void ldb(const float* p, uint32_t& hi, uint32_t& lo) {
+  if (PRE) {
+    const float2 v = *reinterpret_cast<const float2*>(p);
+    hi = __float_as_uint(v.x);
+    lo = __float_as_uint(v.y);
+  } else {
+    const float v = *p;
+    hi = __float_as_uint(v);
+    lo = tf32_lo(v);
+  }
+}
+
+// out[KS][4] = P[NT][.] (accumulator layout, keys permuted) times X (shared, row stride SV elements).
 // Two key tiles and all DH/8 output tiles are issued interleaved per split term; even / odd key tiles
 // accumulate into separate registers, so every accumulator is touched once per 2*KS MMAs.
-template <int DH, int NT>
+template <int DH, int E, int NT>
 __device__ __forceinline__ void pv_product(const float (&P)[NT][4], const float* Xs, float (&out)[DH / 8][4], int g,
                                            int t) {
-  constexpr int KS = DH / 8, SK = DH + 4;
+  using LY = AttnMmaLayout<DH, E>;
+  constexpr int KS = DH / 8, SV = LY::SV, PS = LY::PS;
+  constexpr bool PRE = LY::PRE;
   float acc[2][KS][4];
 #pragma unroll
   for (int p = 0; p < 2; ++p)
@@ -85,7 +116,7 @@ __device__ __forceinline__ void pv_product(const float (&P)[NT][4], const float*
 #pragma unroll
   for (int nt0 = 0; nt0 < NT; nt0 += 2) {
     uint32_t ph[2][4], pl[2][4];
-    float b0[2][KS], b1[2][KS];
+    uint32_t bh0[2][KS], bh1[2][KS], bl0[2][KS], bl1[2][KS];
 #pragma unroll
     for (int p = 0; p < 2; ++p)
       if (nt0 + p < NT) {
@@ -93,26 +124,26 @@ __device__ __forceinline__ void pv_product(const float (&P)[NT][4], const float*
         split4(pa, ph[p], pl[p]);
 #pragma unroll
         for (int n = 0; n < KS; ++n) {
-          const float* xp = Xs + ((nt0 + p) * 8 + 2 * t) * SK + n * 8 + g;
-          b0[p][n] = xp[0];
-          b1[p][n] = xp[SK];
+          const float* xp = Xs + (((nt0 + p) * 8 + 2 * t) * SV + n * 8 + g) * PS;
+          ldb<PRE>(xp, bh0[p][n], bl0[p][n]);
+          ldb<PRE>(xp + SV * PS, bh1[p][n], bl1[p][n]);
         }
       }
 #pragma unroll
     for (int p = 0; p < 2; ++p)
       if (nt0 + p < NT)
 #pragma unroll
-        for (int n = 0; n < KS; ++n) mma_tf32(acc[p][n], pl[p], __float_as_uint(b0[p][n]), __float_as_uint(b1[p][n]));
+        for (int n = 0; n < KS; ++n) mma_tf32(acc[p][n], pl[p], bh0[p][n], bh1[p][n]);
 #pragma unroll
     for (int p = 0; p < 2; ++p)
       if (nt0 + p < NT)
 #pragma unroll
-        for (int n = 0; n < KS; ++n) mma_tf32(acc[p][n], ph[p], tf32_lo(b0[p][n]), tf32_lo(b1[p][n]));
+        for (int n = 0; n < KS; ++n) mma_tf32(acc[p][n], ph[p], bl0[p][n], bl1[p][n]);
 #pragma unroll
     for (int p = 0; p < 2; ++p)
       if (nt0 + p < NT)
 #pragma unroll
-        for (int n = 0; n < KS; ++n) mma_tf32(acc[p][n], ph[p], __float_as_uint(b0[p][n]), __float_as_uint(b1[p][n]));
+        for (int n = 0; n < KS; ++n) mma_tf32(acc[p][n], ph[p], bh0[p][n], bh1[p][n]);
   }
 #pragma unroll
   for (int n = 0; n < KS; ++n)
@@ -124,21 +155,22 @@ __device__ __forceinline__ void pv_product(const float (&P)[NT][4], const float*
 template <int DH, int E, int NT>
 __global__ void __launch_bounds__(256, (NT <= 16) ? 2 : 1) attention_mma_kernel(AttnArgs a) {
   using LY = AttnMmaLayout<DH, E>;
-  constexpr int SK = LY::SK, SE = LY::SE, NC = LY::NC, SW = LY::SW;
+  constexpr int SK = LY::SK, SV = LY::SV, SE = LY::SE, NC = LY::NC, SW = LY::SW, PS = LY::PS;
+  constexpr bool PRE = LY::PRE;
   constexpr int KS = DH / 8;   // k-steps over the head dim / n-tiles of a [.,DH] output
   constexpr int ES = E / 8;    // k-steps over events
   constexpr int LP = NT * 8;   // padded key count
   extern __shared__ __align__(16) float smem[];
-  float* Ks = smem;
-  float* Vs = Ks + LP * SK;
-  float* Ts = Vs + LP * SK;
-  float* Ms = Ts + LP * SK;          // [LP][SE] marks as float (tf.to_float, temporal.py:311)
-  float* W1 = Ms + LP * SE;          // [DH][SW]  rows 0..DH-1 of int_w
-  float* wsp = W1 + DH * SW;         // [NC] row DH of int_w (multiplies the interval)
-  float* b1 = wsp + NC;              // [NC]
+  float* Ks = smem;                  // [LP][SK] x PS
+  float* Vs = Ks + LP * SK * PS;     // [LP][SV] x PS
+  float* Ts = Vs + LP * SV * PS;     // [LP][SV] x PS
+  float* W1 = Ts + LP * SV * PS;     // [DH][SW] x PS   rows 0..DH-1 of int_w, times -log2(e)
+  float* Ms = W1 + DH * SW * PS;     // [LP][SE] marks as float (tf.to_float, temporal.py:311)
+  float* wsp = Ms + LP * SE;         // [NC] row DH of int_w (multiplies the interval), times -log2(e)
+  float* b1 = wsp + NC;              // [NC] times -log2(e)
   float* wv = b1 + NC;               // [NC] int_weight flattened [E][DH]
   float* sc = wv + NC;               // [E] exp(scaling)
-  float* km = sc + E;                // [LP] 1 = real key, 0 = padding id, -1 = beyond L
+  float* km = sc + E;                // [LP] min-mask: +inf real key, fill = masked id, -inf = beyond L
 
   const int L = a.L, B = a.B;
   const int b = blockIdx.x / a.h, hh = blockIdx.x % a.h;
@@ -147,6 +179,14 @@ __global__ void __launch_bounds__(256, (NT <= 16) ? 2 : 1) attention_mma_kernel(
   const long long row0 = (long long)b * L;
 
   // ---------------------------------------------------------------- stage operands in shared memory
+  auto put = [](float* dst, float x) {  // one element: (hi, lo) pair or plain
+    if (PRE) {
+      dst[0] = x;
+      dst[1] = __uint_as_float(tf32_lo(x));
+    } else {
+      dst[0] = x;
+    }
+  };
   constexpr int V4 = DH / 4;
   for (int i = tid; i < LP * V4; i += nthr) {
     const int k = i / V4, j = (i % V4) * 4;
@@ -157,18 +197,22 @@ __global__ void __launch_bounds__(256, (NT <= 16) ? 2 : 1) attention_mma_kernel(
       vv = *reinterpret_cast<const float4*>(a.V + r * a.ldv + hh * DH + j);
       tt = *reinterpret_cast<const float4*>(a.T + r * a.ldt + hh * DH + j);
     }
-    *reinterpret_cast<float4*>(Ks + k * SK + j) = kk;
-    *reinterpret_cast<float4*>(Vs + k * SK + j) = vv;
-    *reinterpret_cast<float4*>(Ts + k * SK + j) = tt;
+    const float ka[4] = {kk.x, kk.y, kk.z, kk.w}, va[4] = {vv.x, vv.y, vv.z, vv.w}, ta[4] = {tt.x, tt.y, tt.z, tt.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      put(Ks + (k * SK + j + e) * PS, ka[e]);
+      put(Vs + (k * SV + j + e) * PS, va[e]);
+      put(Ts + (k * SV + j + e) * PS, ta[e]);
+    }
   }
   for (int i = tid; i < LP * E; i += nthr) {
     const int k = i / E, e = i % E;
     Ms[k * SE + e] = (k < L) ? (float)a.marks[(row0 + k) * E + e] : 0.f;
   }
-  for (int i = tid; i < LP; i += nthr) km[i] = (i < L) ? (a.kmask[row0 + i] ? 1.f : 0.f) : -1.f;
+  for (int i = tid; i < LP; i += nthr) km[i] = (i < L) ? (a.kmask[row0 + i] ? INFINITY : kFillMma) : -INFINITY;
   // The MLP operands are staged pre-multiplied by -log2(e): the MMA then yields -z*log2(e) directly and
   // sigmoid(z) = 1 / (1 + 2^(-z log2 e)) costs one ex2, one add, one rcp (tf.nn.sigmoid, temporal.py:290).
-  for (int i = tid; i < DH * NC; i += nthr) W1[(i / NC) * SW + (i % NC)] = -kLog2e * a.int_w[i];
+  for (int i = tid; i < DH * NC; i += nthr) put(W1 + ((i / NC) * SW + (i % NC)) * PS, -kLog2e * a.int_w[i]);
   for (int i = tid; i < NC; i += nthr) {
     wsp[i] = -kLog2e * a.int_w[DH * NC + i];
     b1[i] = -kLog2e * a.int_b[i];
@@ -205,23 +249,23 @@ __global__ void __launch_bounds__(256, (NT <= 16) ? 2 : 1) attention_mma_kernel(
     for (int n0 = 0; n0 < NT; n0 += 4) {
 #pragma unroll
       for (int ks = 0; ks < KS; ++ks) {
-        float b0[4], b1[4];
+        uint32_t bh0[4], bh1[4], bl0[4], bl1[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j)
           if (n0 + j < NT) {
-            const float* kp = Ks + ((n0 + j) * 8 + g) * SK + ks * 8 + t;
-            b0[j] = kp[0];
-            b1[j] = kp[4];
+            const float* kp = Ks + (((n0 + j) * 8 + g) * SK + ks * 8 + t) * PS;
+            ldb<PRE>(kp, bh0[j], bl0[j]);
+            ldb<PRE>(kp + 4 * PS, bh1[j], bl1[j]);
           }
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          if (n0 + j < NT) mma_tf32(P[n0 + j], ql[ks], __float_as_uint(b0[j]), __float_as_uint(b1[j]));
+          if (n0 + j < NT) mma_tf32(P[n0 + j], ql[ks], bh0[j], bh1[j]);
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          if (n0 + j < NT) mma_tf32(P[n0 + j], qh[ks], tf32_lo(b0[j]), tf32_lo(b1[j]));
+          if (n0 + j < NT) mma_tf32(P[n0 + j], qh[ks], bl0[j], bl1[j]);
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          if (n0 + j < NT) mma_tf32(P[n0 + j], qh[ks], __float_as_uint(b0[j]), __float_as_uint(b1[j]));
+          if (n0 + j < NT) mma_tf32(P[n0 + j], qh[ks], bh0[j], bh1[j]);
       }
     }
     // ---- scale, key mask, causal mask, softmax (rows live in a quad: 2 shuffles per reduction).
@@ -231,15 +275,16 @@ __global__ void __launch_bounds__(256, (NT <= 16) ? 2 : 1) attention_mma_kernel(
     float ma = -INFINITY, mb = -INFINITY;
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
-      const float k0 = km[nt * 8 + 2 * t], k1 = km[nt * 8 + 2 * t + 1];
+      const float2 kmv = *reinterpret_cast<const float2*>(km + nt * 8 + 2 * t);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        const int col = nt * 8 + 2 * t + (c & 1);
-        const int qr = (c < 2) ? qa : qb;
-        const float kmv = (c & 1) ? k1 : k0;
-        float s = P[nt][c] * sc2;
-        if (kmv == 0.f || (a.causal && col > qr)) s = kFillMma;
-        if (kmv < 0.f) s = -INFINITY;  // beyond L: not a key at all
+        // min with +inf (real key) / fill (padding id: the where(mask==0, -2^32+1, .) of temporal.py:425-426)
+        // / -inf (column beyond L)
+        float s = fminf(P[nt][c] * sc2, (c & 1) ? kmv.y : kmv.x);
+        if (a.causal) {
+          const int col = nt * 8 + 2 * t + (c & 1);
+          if (col > ((c < 2) ? qa : qb)) s = fminf(s, kFillMma);  // temporal.py:362-367
+        }
         P[nt][c] = s;
         if (c < 2) ma = fmaxf(ma, s); else mb = fmaxf(mb, s);
       }
@@ -269,7 +314,7 @@ __global__ void __launch_bounds__(256, (NT <= 16) ? 2 : 1) attention_mma_kernel(
     }
     // ---- H = P T   (k = keys, permuted: slot t <-> key 2t, slot t+4 <-> key 2t+1)
     float H[KS][4];
-    pv_product<DH, NT>(P, Ts, H, g, t);
+    pv_product<DH, E, NT>(P, Ts, H, g, t);
     // ---- intensity MLP: Z = sigmoid([H, span] W1 + b1); dot with w per event (temporal.py:287-305)
     const float spa = a.spans[ra], spb = a.spans[rb];
     uint32_t hh_[KS][4], hl_[KS][4];
@@ -289,23 +334,23 @@ __global__ void __launch_bounds__(256, (NT <= 16) ? 2 : 1) attention_mma_kernel(
         for (int j = 0; j < 4; ++j) z[j][0] = z[j][1] = z[j][2] = z[j][3] = 0.f;
 #pragma unroll
         for (int ks = 0; ks < KS; ++ks) {
-          float b0[4], b1[4];
+          uint32_t bh0[4], bh1[4], bl0[4], bl1[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             if (tg + j < MT) {
-              const float* wp = W1 + (ks * 8 + 2 * t) * SW + (tg + j) * 8 + g;
-              b0[j] = wp[0];
-              b1[j] = wp[SW];
+              const float* wp = W1 + ((ks * 8 + 2 * t) * SW + (tg + j) * 8 + g) * PS;
+              ldb<PRE>(wp, bh0[j], bl0[j]);
+              ldb<PRE>(wp + SW * PS, bh1[j], bl1[j]);
             }
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            if (tg + j < MT) mma_tf32(z[j], hl_[ks], __float_as_uint(b0[j]), __float_as_uint(b1[j]));
+            if (tg + j < MT) mma_tf32(z[j], hl_[ks], bh0[j], bh1[j]);
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            if (tg + j < MT) mma_tf32(z[j], hh_[ks], tf32_lo(b0[j]), tf32_lo(b1[j]));
+            if (tg + j < MT) mma_tf32(z[j], hh_[ks], bl0[j], bl1[j]);
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            if (tg + j < MT) mma_tf32(z[j], hh_[ks], __float_as_uint(b0[j]), __float_as_uint(b1[j]));
+            if (tg + j < MT) mma_tf32(z[j], hh_[ks], bh0[j], bh1[j]);
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -349,8 +394,11 @@ __global__ void __launch_bounds__(256, (NT <= 16) ? 2 : 1) attention_mma_kernel(
         if (t == 2) { xa = lsa[ebase + 2]; xb = lsb[ebase + 2]; }
         if (t == 3) { xa = lsa[ebase + 3]; xb = lsb[ebase + 3]; }
         const float s = sc[ebase + t];
-        const float va = s * logf(1.f + expf(__fdiv_rn(xa, s)));
-        const float vb = s * logf(1.f + expf(__fdiv_rn(xb, s)));
+        // naive softplus like the reference (overflows to inf for x/s > 88.7, Q6), on the fast exp2/log2 units:
+        // s*ln(1 + e^(x/s)) = (s ln2) * log2(1 + 2^(x * log2e / s))
+        const float rs = rcp_approx(s) * kLog2e, sl = s * 0.69314718055994531f;
+        const float va = sl * lg2_approx(1.f + ex2_approx(xa * rs));
+        const float vb = sl * lg2_approx(1.f + ex2_approx(xb * rs));
         lam4[hsel * 2 + 0] = va;  // a0 / a2 : row qa
         lam4[hsel * 2 + 1] = vb;  // a1 / a3 : row qb
         if (a.lam) {
@@ -397,7 +445,7 @@ __global__ void __launch_bounds__(256, (NT <= 16) ? 2 : 1) attention_mma_kernel(
     }
     // ---- O = (G o P) V
     float O[KS][4];
-    pv_product<DH, NT>(P, Vs, O, g, t);
+    pv_product<DH, E, NT>(P, Vs, O, g, t);
     // ---- residual + store (temporal.py:385,447)
 #pragma unroll
     for (int n = 0; n < KS; ++n) {

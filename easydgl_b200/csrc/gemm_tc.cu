@@ -16,6 +16,7 @@
 // Pipelines: full[s] (TMA landed) -> split[s] (lo halves written) -> MMA -> empty[s];
 //            tmem_full[a] (tile accumulated) -> epilogue -> tmem_empty[a]  (two TMEM accumulators).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -60,6 +61,11 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
           smem_u32(dst)),
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(map)),
+               "r"(c0), "r"(c1)
+               : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -126,6 +132,7 @@ struct Params {
   int act;
   int col0_bias_only;  // tied zero-padded table: column 0 is exactly the bias (coding.py:56-57)
   int ntn, num_tiles, kblocks;
+  long long* dbg;  // optional [gridDim][8] cycle counters (EDGL_TC_DEBUG), else null
 };
 
 __device__ __forceinline__ float gelu_erf_tc(float x) {
@@ -185,17 +192,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   const uint32_t tmem_base = *tmem_slot;
 
   const int KB = p.kblocks;
+  long long dbg_acc[7] = {0, 0, 0, 0, 0, 0, 0};
+  const long long t_start = clock64();
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapA)) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapB)) : "memory");
       uint32_t it = 0;
+      // the activations stream from HBM exactly once: pull the A rows of the NEXT tile into L2 while the
+      // current tile is computed, so the TMA loads below see L2 latency instead of DRAM latency
+      for (int kb = 0; kb < KB; ++kb) tma_prefetch_2d(&mapA, kb * BK, (blockIdx.x / p.ntn) * BM);
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const int m0 = (tile / p.ntn) * BM, n0 = (tile % p.ntn) * BN;
+        const int ntile = tile + gridDim.x;
         for (int kb = 0; kb < KB; ++kb, ++it) {
           const int s = it % S;
+          if (ntile < p.num_tiles) tma_prefetch_2d(&mapA, kb * BK, (ntile / p.ntn) * BM);
+          const long long t0 = clock64();
           mbar_wait(&empty[s], ((it / S) & 1) ^ 1);
+          dbg_acc[0] += clock64() - t0;
           mbar_expect_tx(&full[s], SM::A_BYTES + SM::B_BYTES);
           tma_load_2d(&mapA, &full[s], stA(s), kb * BK, m0);
           tma_load_2d(&mapB, &full[s], stB(s), kb * BK, n0);
@@ -209,12 +225,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       uint32_t it = 0, tcount = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tcount) {
         const int acc = tcount & 1;
+        long long t0 = clock64();
         mbar_wait(&tempty[acc], ((tcount >> 1) & 1) ^ 1);
+        dbg_acc[1] += clock64() - t0;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < KB; ++kb, ++it) {
           const int s = it % S;
+          t0 = clock64();
           mbar_wait(&split[s], (it / S) & 1);
+          dbg_acc[2] += clock64() - t0;
           tc_fence_after();
           const uint32_t a_hi = smem_u32(stA(s)), a_lo = smem_u32(stAlo(s));
           const uint32_t b_hi = smem_u32(stB(s)), b_lo = smem_u32(stBlo(s));
@@ -239,7 +259,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       for (int kb = 0; kb < KB; ++kb, ++it) {
         const int s = it % S;
+        long long t0 = clock64();
         mbar_wait(&full[s], (it / S) & 1);
+        const long long t1 = clock64();
+        dbg_acc[3] += t1 - t0;
         const float4* a = reinterpret_cast<const float4*>(stA(s));
         float4* al = reinterpret_cast<float4*>(stAlo(s));
         const float4* b = reinterpret_cast<const float4*>(stB(s));
@@ -258,6 +281,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         for (int i = t; i < SM::B_BYTES / 16; i += 128) bl[i] = lo4(b[i]);
         fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
         mbar_arrive(&split[s]);
+        dbg_acc[4] += clock64() - t1;
       }
     }
   } else if (warp >= 4) {
@@ -295,7 +319,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           if (pr >= p.pperiod) pr -= p.pperiod;
         }
       }
+      const long long t0 = clock64();
       mbar_wait(&tfull[acc], (tcount >> 1) & 1);
+      const long long t1 = clock64();
+      dbg_acc[5] += t1 - t0;
       tc_fence_after();
 #pragma unroll 1
       for (int c0 = half * CW; c0 < BN; c0 += 2 * CW) {
@@ -363,7 +390,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       }
       tc_fence_before();
       mbar_arrive(&tempty[acc]);
+      dbg_acc[6] += clock64() - t1;
     }
+  }
+  if (p.dbg && lane == 0 && (warp == 0 || warp == 1 || warp == 4 || warp == 12)) {
+    for (int i = 0; i < 7; ++i)
+      if (dbg_acc[i]) p.dbg[blockIdx.x * 8 + i] = dbg_acc[i];
+    if (warp == 0) p.dbg[blockIdx.x * 8 + 7] = clock64() - t_start;
   }
   tc_fence_before();
   __syncthreads();
@@ -439,6 +472,14 @@ int launch_gemm_tc(const GemmArgs& a, cudaStream_t st) {
   p.num_tiles = (int)(ntm * p.ntn);
   p.kblocks = cdiv(a.K, BK);
   const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
+  p.dbg = nullptr;
+  static const bool debug = getenv("EDGL_TC_DEBUG") != nullptr;
+  static long long* dbg_buf = nullptr;
+  if (debug) {
+    if (!dbg_buf) cudaMalloc(&dbg_buf, 8 * 256 * sizeof(long long));
+    cudaMemsetAsync(dbg_buf, 0, 8 * 256 * sizeof(long long), st);
+    p.dbg = dbg_buf;
+  }
 #define EDGL_TC_LAUNCH(BNV, ACTV)                                                                              \
   {                                                                                                            \
     auto kern = gemm_tc_kernel<BNV, ACTV>;                                                                     \
@@ -456,6 +497,18 @@ int launch_gemm_tc(const GemmArgs& a, cudaStream_t st) {
   }
 #undef EDGL_TC_LAUNCH
   EDGL_LAUNCH_CHECK();
+  if (debug) {
+    long long hbuf[8 * 256];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(hbuf, dbg_buf, sizeof(hbuf), cudaMemcpyDeviceToHost);
+    double s7[8] = {0};
+    for (int b = 0; b < grid; ++b)
+      for (int i = 0; i < 8; ++i) s7[i] += (double)hbuf[b * 8 + i] / grid;
+    fprintf(stderr,
+            "[tc] M=%d N=%d K=%d bn=%d tiles/cta=%.1f | cycles/CTA: total %.0f | producer wait_empty %.0f | mma wait_tempty "
+            "%.0f wait_split %.0f | splitter wait_full %.0f work %.0f | epilogue wait_tfull %.0f work %.0f\n",
+            a.M, a.N, a.K, bn, (double)p.num_tiles / grid, s7[7], s7[0], s7[1], s7[2], s7[3], s7[4], s7[5], s7[6]);
+  }
   return 0;
 }
 

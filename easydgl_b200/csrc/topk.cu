@@ -59,23 +59,37 @@ __device__ void bitonic_desc(unsigned long long* s, int n) {
   __syncthreads();
 }
 
-// One CTA (256 threads) per row.  dynamic smem: KP u64 candidates.
-__global__ void __launch_bounds__(256) topk_kernel(const float* __restrict__ logits, int ld, int N, int K, int KP,
-                                                   int col_offset, int32_t* __restrict__ idx_out,
-                                                   float* __restrict__ val_out) {
-  extern __shared__ __align__(16) unsigned long long cand[];
+// first K entries of the sorted candidate list -> (global index, value); pad when fewer than K exist
+__device__ __forceinline__ void write_topk(const unsigned long long* cand, int Keff, int K, int col_offset,
+                                           int32_t* __restrict__ idx_out, float* __restrict__ val_out) {
+  for (int i = threadIdx.x; i < K; i += blockDim.x) {
+    if (i < Keff) {
+      const unsigned long long c = cand[i];
+      idx_out[i] = (int32_t)(0xffffffffu - (uint32_t)(c & 0xffffffffull)) + col_offset;
+      val_out[i] = key2f((uint32_t)(c >> 32));
+    } else {
+      idx_out[i] = -1;
+      val_out[i] = -INFINITY;
+    }
+  }
+}
+
+// Exact radix select of one row (any N, any tie pattern): 4 passes of 8-bit histograms over the
+// order-preserving keys, then an index-ordered pass for the ties at the K-th value, then a bitonic sort.
+// One CTA (256 threads); cand = KP u64 in shared memory.
+__device__ void topk_row_radix(const float* __restrict__ p, int N, int K, int KP, int col_offset,
+                               unsigned long long* cand, int32_t* __restrict__ idx_out, float* __restrict__ val_out) {
   __shared__ unsigned int hist[256];
-  __shared__ unsigned int s_prefix, s_remaining, s_eq_total, s_gt_cnt, s_eq_cnt;
+  __shared__ unsigned int s_prefix, s_remaining, s_eq_total, s_gt_cnt;
   __shared__ unsigned int warp_tot[8];
-  const float* p = logits + (long long)blockIdx.x * ld;
   const int tid = threadIdx.x;
   const int Keff = K < N ? K : N;
+  __syncthreads();
 
   if (tid == 0) {
     s_prefix = 0;
     s_remaining = Keff;
     s_gt_cnt = 0;
-    s_eq_cnt = 0;
   }
   for (int i = tid; i < KP; i += 256) cand[i] = 0ull;
   uint32_t mask = 0;
@@ -151,17 +165,75 @@ __global__ void __launch_bounds__(256) topk_kernel(const float* __restrict__ log
     }
   }
   bitonic_desc(cand, KP);
-  for (int i = tid; i < K; i += 256) {
-    const long long o = (long long)blockIdx.x * K + i;
-    if (i < Keff) {
-      const unsigned long long c = cand[i];
-      idx_out[o] = (int32_t)(0xffffffffu - (uint32_t)(c & 0xffffffffull)) + col_offset;
-      val_out[o] = key2f((uint32_t)(c >> 32));
-    } else {  // fewer than K columns: pad
-      idx_out[o] = -1;
-      val_out[o] = -INFINITY;
+  write_topk(cand, Keff, K, col_offset, idx_out, val_out);
+}
+
+// Fast path for K <= 256 <= N: every thread takes the maximum of its strided slice; the K-th largest of
+// the 256 slice maxima is a LOWER bound t0 of the row's K-th largest value (at least K elements are
+// >= t0), so {x >= t0} contains the whole top-K including every tie at the cut.  Typically ~1.3 K
+// candidates survive; they are sorted exactly (key desc, index asc).  Rows that overflow the candidate
+// buffer (constant rows, everything masked) take the radix path.  Two coalesced reads of the row.
+constexpr int kCandCap = 1024;
+
+__global__ void __launch_bounds__(256) topk_kernel(const float* __restrict__ logits, int ld, int N, int K, int KP,
+                                                   int col_offset, int32_t* __restrict__ idx_out,
+                                                   float* __restrict__ val_out) {
+  extern __shared__ __align__(16) unsigned long long cand[];  // max(KP, kCandCap) entries
+  __shared__ unsigned int s_cnt;
+  __shared__ uint32_t s_t0;
+  const float* p = logits + (long long)blockIdx.x * ld;
+  int32_t* io = idx_out + (long long)blockIdx.x * K;
+  float* vo = val_out + (long long)blockIdx.x * K;
+  const int tid = threadIdx.x;
+  if (K > 256 || N < 1024) {
+    topk_row_radix(p, N, K, KP, col_offset, cand, io, vo);
+    return;
+  }
+  const bool vec = (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(logits) & 15) == 0);
+  const int N4 = vec ? (N >> 2) : 0;
+  // ---- pass 1: slice maxima
+  uint32_t mx = 0;
+  for (int i = tid; i < N4; i += 256) {
+    const float4 v = reinterpret_cast<const float4*>(p)[i];
+    mx = max(max(mx, f2key(v.x)), max(f2key(v.y), max(f2key(v.z), f2key(v.w))));
+  }
+  for (int i = 4 * N4 + tid; i < N; i += 256) mx = max(mx, f2key(p[i]));
+  cand[tid] = (unsigned long long)mx;
+  if (tid == 0) s_cnt = 0;
+  bitonic_desc(cand, 256);
+  if (tid == 0) s_t0 = (uint32_t)cand[K - 1];
+  __syncthreads();
+  const uint32_t t0 = s_t0;
+  __syncthreads();
+  // ---- pass 2: collect {key >= t0}
+  for (int i = tid; i < N4; i += 256) {
+    const float4 v = reinterpret_cast<const float4*>(p)[i];
+    const uint32_t k4[4] = {f2key(v.x), f2key(v.y), f2key(v.z), f2key(v.w)};
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      if (k4[e] >= t0) {
+        const unsigned int pos = atomicAdd(&s_cnt, 1u);
+        if (pos < kCandCap) cand[pos] = compose(k4[e], (uint32_t)(4 * i + e));
+      }
+  }
+  for (int i = 4 * N4 + tid; i < N; i += 256) {
+    const uint32_t k = f2key(p[i]);
+    if (k >= t0) {
+      const unsigned int pos = atomicAdd(&s_cnt, 1u);
+      if (pos < kCandCap) cand[pos] = compose(k, (uint32_t)i);
     }
   }
+  __syncthreads();
+  const unsigned int cnt = s_cnt;
+  if (cnt > kCandCap) {  // block-uniform
+    topk_row_radix(p, N, K, KP, col_offset, cand, io, vo);
+    return;
+  }
+  int np = 128;
+  while (np < (int)cnt) np <<= 1;
+  for (int i = cnt + tid; i < np; i += 256) cand[i] = 0ull;
+  bitonic_desc(cand, np);
+  write_topk(cand, K, K, col_offset, io, vo);
 }
 
 static int next_pow2(int v) {
@@ -176,7 +248,8 @@ int launch_topk(const float* logits, int ld, int B, int N, int K, int col_offset
   EDGL_REQUIRE(N >= 1, "topk: N must be >= 1");
   if (B == 0) return 0;
   const int KP = next_pow2(K);
-  topk_kernel<<<B, 256, (size_t)KP * 8, st>>>(logits, ld, N, K, KP, col_offset, idx, val);
+  const size_t smem = (size_t)(KP > kCandCap ? KP : kCandCap) * 8;
+  topk_kernel<<<B, 256, smem, st>>>(logits, ld, N, K, KP, col_offset, idx, val);
   EDGL_LAUNCH_CHECK();
   return 0;
 }

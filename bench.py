@@ -42,7 +42,8 @@ def workload_desc(cfg, B, n_gpus):
                        cfg.num_events, cfg.topk),
         "global_batch": B * n_gpus,
         "parallelism": "single GPU" if n_gpus == 1 else
-        "batch-sharded encoder + column-sharded item table (%d shards), 2 NCCL all-gathers" % n_gpus,
+        "batch-sharded encoder + column-sharded item table (%d shards); NCCL all-gather of [y|ids] rows, then "
+        "exchange of per-shard top-K candidates + local merge" % n_gpus,
         "l2": "per-step working set ~3 GB of activations >> 126 MB L2; %d rotating input batches" % NUM_INPUT_SETS,
         "weights": "reference initialisers (glorot / N(0,0.02)), seed 9876",
     }
@@ -175,7 +176,7 @@ def run_reference(args):
         "note": "the reference needs tensorflow-gpu==2.3.4 (not installable here); this arm times oracle/, the "
                 "op-for-op CPU restatement of its forward path, with all host threads",
     }
-    print(json.dumps(line), flush=True)
+    _emit(args.out_fd, line)
     return 0
 
 
@@ -203,7 +204,7 @@ def run_ours(args):
     ranker = None
     if world > 1:
         from easydgl_b200.sharded import ShardedRanker
-        ranker = ShardedRanker(eng)
+        ranker = ShardedRanker(eng, exchange=args.exchange)
 
     sets = []
     for i in range(NUM_INPUT_SETS):
@@ -348,7 +349,7 @@ def run_ours(args):
                 "value": sps, "unit": "seq/s", "cores": threads, "kind": "port",
                 "sample": "%d steps x %d sequences of the %s workload (%.1f s), fp32 torch-CPU oracle, contracted gate"
                           % (args.cpu_steps, n_seqs, WORKLOAD, step_s * args.cpu_steps)}
-        print(json.dumps(line), flush=True)
+        _emit(args.out_fd, line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -356,6 +357,24 @@ def run_ours(args):
 
 
 def main():
+    # Libraries (NCCL's version banner, torchrun) may write to fd 1: park the real stdout and route fd 1 to
+    # stderr for the whole run, so that stdout carries exactly ONE line - the JSON result.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        rc = _main(real_stdout)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+    return rc
+
+
+def _emit(fd, line):
+    os.write(fd, (json.dumps(line) + "\n").encode())
+
+
+def _main(out_fd):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
@@ -364,7 +383,10 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="override per-GPU batch (debug only)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-steps", type=int, default=20)
+    ap.add_argument("--exchange", default="all_to_all", choices=["all_to_all", "all_gather"],
+                    help="candidate exchange of the column-sharded multi-GPU path")
     args = ap.parse_args()
+    args.out_fd = out_fd
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)

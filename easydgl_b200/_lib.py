@@ -43,8 +43,8 @@ _SIGS = {
     "edgl_forward_topk": (_I, [_P, _P, _P, _I, _I, _P, _P, _P]),
     "edgl_forward_topk_host": (_I, [_P, _P, _P, _I, _I, _P, _P, _P]),
     "edgl_encode": (_I, [_P, _P, _P, _I, _P, _P]),
-    "edgl_logits_topk": (_I, [_P, _P, _P, _I, _I, _P, _P, _P]),
-    "edgl_topk_merge": (_I, [_P, _P, _I, _I, _I, C.c_int64, _P, _P, _P]),
+    "edgl_logits_topk": (_I, [_P, _P, C.c_int64, _P, _I, C.c_int64, _I, C.c_int64, _P, _P, _P]),
+    "edgl_topk_merge": (_I, [_P, _P, _I, _I, _I, C.c_int64, C.c_int64, _P, _P, _P]),
     "edgl_time_sinusoid_code": (_I, [_P, _I, _I, _I, _P, _P]),
     "edgl_embedding_lookup": (_I, [_P, _I, _I, _I, _I, _P, C.c_int64, _P, _P]),
     "edgl_embed": (_I, [_P, _P, _P, _I, _P, _P, _P, _P]),

@@ -315,9 +315,9 @@ int encode(edgl_handle* h, const int64_t* ids, const float* ts, int B, float* y,
 }
 
 // logits[r0:r0+rc, c0:c1] = y @ table[c0:c1]^T + bias   (EasyDGL.py:149-150 / CTSMA.py:89-90, Base.py:106-110)
-int logits_rows(edgl_handle* h, const float* y, long long rc, float* out, int ldo, cudaStream_t st) {
+int logits_rows(edgl_handle* h, const float* y, int ldy, long long rc, float* out, int ldo, cudaStream_t st) {
   GemmArgs g;
-  g.A = y; g.lda = h->d;
+  g.A = y; g.lda = ldy;
   g.W = F(h->mt, "item_embs") + h->c0 * h->d; g.ldw = h->d; g.w_is_nk = true;
   g.zero_wrow0 = (h->c0 == 0);  // zero_pad=True: row 0 of the tied table is zeros (coding.py:56-57)
   g.C = out; g.ldc = ldo; g.M = (int)rc; g.N = (int)(h->c1 - h->c0); g.K = h->d;
@@ -325,20 +325,23 @@ int logits_rows(edgl_handle* h, const float* y, long long rc, float* out, int ld
   return launch_gemm(g, st);
 }
 
-int logits_topk(edgl_handle* h, const float* y, const int64_t* seen, int seen_len, long long Bt, int32_t* idx,
-                float* val, cudaStream_t st) {
+int logits_topk(edgl_handle* h, const float* y, int ldy, const int64_t* seen, int seen_len, long long seen_stride,
+                long long Bt, int32_t* idx, float* val, long long ostride, cudaStream_t st) {
+  if (ostride == 0) ostride = h->K;
+  if (ldy == 0) ldy = h->d;
+  if (seen_stride == 0) seen_stride = seen_len;
   const int Ns = (int)(h->c1 - h->c0);
   const int ldw = (Ns + 3) & ~3;  // padded pitch: vector stores in the GEMM epilogue
   for (long long r0 = 0; r0 < Bt; r0 += h->ws_rows) {
     const long long rc = (Bt - r0 < h->ws_rows) ? (Bt - r0) : h->ws_rows;
     mark(h, ST_LOGITS_GEMM, st);
-    EDGL_TRY(logits_rows(h, y + r0 * h->d, rc, h->logits_ws, ldw, st));
+    EDGL_TRY(logits_rows(h, y + r0 * ldy, ldy, rc, h->logits_ws, ldw, st));
     if (seen) {
       mark(h, ST_MASK_SEEN, st);
-      EDGL_TRY(launch_mask_seen(h->logits_ws, ldw, (int)rc, seen + r0 * seen_len, seen_len, h->c0, h->c1, st));
+      EDGL_TRY(launch_mask_seen(h->logits_ws, ldw, (int)rc, seen + r0 * seen_stride, seen_len, seen_stride, h->c0, h->c1, st));
     }
     mark(h, ST_TOPK, st);
-    EDGL_TRY(launch_topk(h->logits_ws, ldw, (int)rc, Ns, h->K, (int)h->c0, idx + r0 * h->K, val + r0 * h->K, st));
+    EDGL_TRY(launch_topk(h->logits_ws, ldw, (int)rc, Ns, h->K, (int)h->c0, ostride, idx + r0 * ostride, val + r0 * ostride, st));
   }
   mark(h, ST_END, st);
   return 0;
@@ -617,7 +620,7 @@ int edgl_forward_logits(edgl_handle* h, const int64_t* seqs_i, const float* seqs
   cudaStream_t st = (cudaStream_t)stream;
   EDGL_TRY(encode(h, seqs_i, seqs_t, B, h->y, st));
   mark(h, ST_LOGITS_GEMM, st);
-  EDGL_TRY(logits_rows(h, h->y, B, logits, (int)(h->c1 - h->c0), st));
+  EDGL_TRY(logits_rows(h, h->y, h->d, B, logits, (int)(h->c1 - h->c0), st));
   mark(h, ST_END, st);
   return 0;
 }
@@ -631,7 +634,7 @@ int edgl_forward_topk(edgl_handle* h, const int64_t* seqs_i, const float* seqs_t
   if (B == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   EDGL_TRY(encode(h, seqs_i, seqs_t, B, h->y, st));
-  return logits_topk(h, h->y, mask_seen ? seqs_i : nullptr, h->L, B, idx, val, st);
+  return logits_topk(h, h->y, h->d, mask_seen ? seqs_i : nullptr, h->L, h->L, B, idx, val, 0, st);
 }
 
 int edgl_forward_topk_host(edgl_handle* h, const int64_t* seqs_i_host, const float* seqs_t_host, int B,
@@ -649,19 +652,24 @@ int edgl_forward_topk_host(edgl_handle* h, const int64_t* seqs_i_host, const flo
   return 0;
 }
 
-int edgl_logits_topk(edgl_handle* h, const float* y, const int64_t* seen_ids, int seen_len, int Bt,
-                     int32_t* cand_idx, float* cand_val, void* stream) {
+int edgl_logits_topk(edgl_handle* h, const float* y, int64_t y_stride, const int64_t* seen_ids, int seen_len,
+                     int64_t seen_stride, int Bt, int64_t cand_stride, int32_t* cand_idx, float* cand_val,
+                     void* stream) {
   EDGL_TRY(check_ready(h, Bt, false));
   if (!y || !cand_idx || !cand_val) return set_error(EDGL_EINVAL, "null argument");
   EDGL_REQUIRE(!seen_ids || seen_len >= 1, "seen_len must be >= 1");
-  return logits_topk(h, y, seen_ids, seen_len, Bt, cand_idx, cand_val, (cudaStream_t)stream);
+  EDGL_REQUIRE(cand_stride == 0 || cand_stride >= h->K, "cand_stride must be 0 or >= K");
+  EDGL_REQUIRE(y_stride == 0 || (y_stride >= h->d && y_stride % 4 == 0), "y_stride must be 0 or a multiple of 4 >= d");
+  EDGL_REQUIRE(seen_stride == 0 || seen_stride >= seen_len, "seen_stride must be 0 or >= seen_len");
+  return logits_topk(h, y, (int)y_stride, seen_ids, seen_len, seen_stride, Bt, cand_idx, cand_val, cand_stride,
+                     (cudaStream_t)stream);
 }
 
 int edgl_topk_merge(const float* cand_val, const int32_t* cand_idx, int G, int Bt, int K, int64_t shard_stride,
-                    int32_t* idx, float* val, void* stream) {
+                    int64_t row_stride, int32_t* idx, float* val, void* stream) {
   if (!cand_val || !cand_idx || !idx || !val) return set_error(EDGL_EINVAL, "null argument");
-  EDGL_REQUIRE(Bt >= 0 && shard_stride >= 0, "negative batch or stride");
-  return launch_topk_merge(cand_val, cand_idx, G, Bt, K, shard_stride, idx, val, (cudaStream_t)stream);
+  EDGL_REQUIRE(Bt >= 0 && shard_stride >= 0 && row_stride >= 0, "negative batch or stride");
+  return launch_topk_merge(cand_val, cand_idx, G, Bt, K, shard_stride, row_stride, idx, val, (cudaStream_t)stream);
 }
 
 int edgl_time_sinusoid_code(const float* ts, int B, int L, int d, float* out, void* stream) {
@@ -762,8 +770,8 @@ int edgl_topk(float* logits, int B, int N, const int64_t* seen_ids, int seen_len
               void* stream) {
   if (!logits || !idx || !val) return set_error(EDGL_EINVAL, "null argument");
   cudaStream_t st = (cudaStream_t)stream;
-  if (seen_ids) EDGL_TRY(launch_mask_seen(logits, N, B, seen_ids, seen_len, 0, N, st));
-  return launch_topk(logits, N, B, N, K, 0, idx, val, st);
+  if (seen_ids) EDGL_TRY(launch_mask_seen(logits, N, B, seen_ids, seen_len, seen_len, 0, N, st));
+  return launch_topk(logits, N, B, N, K, 0, 0, idx, val, st);
 }
 
 }  // extern "C"

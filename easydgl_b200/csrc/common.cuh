@@ -114,11 +114,11 @@ int launch_intensity(const float* H, const float* spans, const uint8_t* marks, c
 int launch_layernorm(const float* x, const float* gamma, const float* beta, int B, int L, int C, float* out,
                      bool last_only, cudaStream_t st);
 
-int launch_mask_seen(float* logits, int ld, int B, const int64_t* ids, int seen_len, long long col0,
-                     long long col1, cudaStream_t st);
-int launch_topk(const float* logits, int ld, int B, int N, int K, int col_offset, int32_t* idx, float* val,
-                cudaStream_t st);
+int launch_mask_seen(float* logits, int ld, int B, const int64_t* ids, int seen_len, long long seen_stride,
+                     long long col0, long long col1, cudaStream_t st);
+int launch_topk(const float* logits, int ld, int B, int N, int K, int col_offset, long long out_stride, int32_t* idx,
+                float* val, cudaStream_t st);
 int launch_topk_merge(const float* cand_val, const int32_t* cand_idx, int G, int Bt, int K, long long shard_stride,
-                      int32_t* idx, float* val, cudaStream_t st);
+                      long long row_stride, int32_t* idx, float* val, cudaStream_t st);
 
 }  // namespace edgl

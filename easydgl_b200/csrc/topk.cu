@@ -20,20 +20,20 @@ __device__ __forceinline__ unsigned long long compose(uint32_t key, uint32_t idx
   return ((unsigned long long)key << 32) | (unsigned long long)(0xffffffffu - idx);
 }
 
-__global__ void mask_seen_kernel(float* __restrict__ logits, int ld, long long n, int seen_len,
+__global__ void mask_seen_kernel(float* __restrict__ logits, int ld, long long n, int seen_len, long long seen_stride,
                                  const int64_t* __restrict__ ids, long long col0, long long col1) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const long long b = i / seen_len;
-  const long long id = ids[i];
+  const long long id = ids[b * seen_stride + (i - b * seen_len)];
   if (id >= col0 && id < col1) logits[b * ld + (id - col0)] = -INFINITY;
 }
 
-int launch_mask_seen(float* logits, int ld, int B, const int64_t* ids, int seen_len, long long col0,
-                     long long col1, cudaStream_t st) {
+int launch_mask_seen(float* logits, int ld, int B, const int64_t* ids, int seen_len, long long seen_stride,
+                     long long col0, long long col1, cudaStream_t st) {
   const long long n = (long long)B * seen_len;
   if (n == 0) return 0;
-  mask_seen_kernel<<<cdiv(n, 256), 256, 0, st>>>(logits, ld, n, seen_len, ids, col0, col1);
+  mask_seen_kernel<<<cdiv(n, 256), 256, 0, st>>>(logits, ld, n, seen_len, seen_stride, ids, col0, col1);
   EDGL_LAUNCH_CHECK();
   return 0;
 }
@@ -54,6 +54,59 @@ __device__ void bitonic_desc(unsigned long long* s, int n) {
           }
         }
       }
+    }
+  }
+  __syncthreads();
+}
+
+// ---- warp-shuffle stages of the same bitonic network (element index i, stage k, distance j <= 16)
+__device__ __forceinline__ unsigned long long cmpx64(unsigned long long v, int i, int k, int j) {
+  const unsigned long long o = __shfl_xor_sync(0xffffffffu, v, j);
+  const bool take_max = (((i & j) == 0) == ((i & k) == 0));  // lower partner of a descending block keeps the max
+  return take_max ? (v > o ? v : o) : (v < o ? v : o);
+}
+__device__ __forceinline__ uint32_t cmpx32(uint32_t v, int i, int k, int j) {
+  const uint32_t o = __shfl_xor_sync(0xffffffffu, v, j);
+  const bool take_max = (((i & j) == 0) == ((i & k) == 0));
+  return take_max ? max(v, o) : min(v, o);
+}
+
+// Descending bitonic sort of n (power of two, >= 32) u64 in shared memory by 256 threads: every
+// compare-exchange at distance <= 16 runs in registers with warp shuffles (no barrier); only the
+// log2(n)-5 long-distance steps of the last stages touch shared memory between barriers.
+__device__ void bitonic_desc_hybrid(unsigned long long* s, int n) {
+  const int lane = threadIdx.x & 31;
+  __syncthreads();
+  for (int base = (threadIdx.x >> 5) * 32; base < n; base += 256) {
+    const int i = base + lane;
+    unsigned long long v = s[i];
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1)
+#pragma unroll
+      for (int j = k >> 1; j > 0; j >>= 1) v = cmpx64(v, i, k, j);
+    s[i] = v;
+  }
+  for (int k = 64; k <= n; k <<= 1) {
+    for (int j = k >> 1; j >= 32; j >>= 1) {
+      __syncthreads();
+      for (int i = threadIdx.x; i < n; i += 256) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const unsigned long long a = s[i], b = s[ixj];
+          if (((i & k) == 0) ? (a < b) : (a > b)) {
+            s[i] = b;
+            s[ixj] = a;
+          }
+        }
+      }
+    }
+    __syncthreads();
+    for (int base = (threadIdx.x >> 5) * 32; base < n; base += 256) {
+      const int i = base + lane;
+      unsigned long long v = s[i];
+#pragma unroll
+      for (int j = 16; j > 0; j >>= 1) v = cmpx64(v, i, k, j);
+      s[i] = v;
     }
   }
   __syncthreads();
@@ -168,22 +221,22 @@ __device__ void topk_row_radix(const float* __restrict__ p, int N, int K, int KP
   write_topk(cand, Keff, K, col_offset, idx_out, val_out);
 }
 
-// Fast path for K <= 256 <= N: every thread takes the maximum of its strided slice; the K-th largest of
-// the 256 slice maxima is a LOWER bound t0 of the row's K-th largest value (at least K elements are
-// >= t0), so {x >= t0} contains the whole top-K including every tie at the cut.  Typically ~1.3 K
-// candidates survive; they are sorted exactly (key desc, index asc).  Rows that overflow the candidate
+// Fast path for K <= 256, N >= 1024: every thread takes the maximum of its strided slice; a threshold t0
+// derived from the slice maxima (see below) is a LOWER bound of the row's K-th largest value (at least K
+// elements are >= t0), so {x >= t0} contains the whole top-K including every tie at the cut.  Typically
+// ~1.9 K candidates survive; they are sorted exactly (key desc, index asc).  Rows that overflow the candidate
 // buffer (constant rows, everything masked) take the radix path.  Two coalesced reads of the row.
 constexpr int kCandCap = 1024;
 
 __global__ void __launch_bounds__(256) topk_kernel(const float* __restrict__ logits, int ld, int N, int K, int KP,
-                                                   int col_offset, int32_t* __restrict__ idx_out,
-                                                   float* __restrict__ val_out) {
+                                                   int col_offset, long long out_stride,
+                                                   int32_t* __restrict__ idx_out, float* __restrict__ val_out) {
   extern __shared__ __align__(16) unsigned long long cand[];  // max(KP, kCandCap) entries
   __shared__ unsigned int s_cnt;
-  __shared__ uint32_t s_t0;
+  __shared__ uint32_t s_t0, s_wt[8];
   const float* p = logits + (long long)blockIdx.x * ld;
-  int32_t* io = idx_out + (long long)blockIdx.x * K;
-  float* vo = val_out + (long long)blockIdx.x * K;
+  int32_t* io = idx_out + (long long)blockIdx.x * out_stride;
+  float* vo = val_out + (long long)blockIdx.x * out_stride;
   const int tid = threadIdx.x;
   if (K > 256 || N < 1024) {
     topk_row_radix(p, N, K, KP, col_offset, cand, io, vo);
@@ -198,13 +251,26 @@ __global__ void __launch_bounds__(256) topk_kernel(const float* __restrict__ log
     mx = max(max(mx, f2key(v.x)), max(f2key(v.y), max(f2key(v.z), f2key(v.w))));
   }
   for (int i = 4 * N4 + tid; i < N; i += 256) mx = max(mx, f2key(p[i]));
-  cand[tid] = (unsigned long long)mx;
-  if (tid == 0) s_cnt = 0;
-  bitonic_desc(cand, 256);
-  if (tid == 0) s_t0 = (uint32_t)cand[K - 1];
+  // per-warp: the q-th largest of the 32 slice maxima, q = ceil(K/8); the minimum of those over the 8
+  // warps has at least 8*q >= K elements at or above it -> a valid lower bound of the K-th largest value
+  {
+    const int lane = tid & 31;
+    uint32_t v = mx;
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1)
+#pragma unroll
+      for (int j = k >> 1; j > 0; j >>= 1) v = cmpx32(v, lane, k, j);  // lanes < 32: the last stage is descending
+    const int q = (K + 7) >> 3;
+    if (lane == q - 1) s_wt[tid >> 5] = v;
+    if (tid == 0) s_cnt = 0;
+    __syncthreads();
+    uint32_t t = s_wt[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) t = min(t, s_wt[w]);
+    if (tid == 0) s_t0 = t;
+  }
   __syncthreads();
   const uint32_t t0 = s_t0;
-  __syncthreads();
   // ---- pass 2: collect {key >= t0}
   for (int i = tid; i < N4; i += 256) {
     const float4 v = reinterpret_cast<const float4*>(p)[i];
@@ -232,7 +298,7 @@ __global__ void __launch_bounds__(256) topk_kernel(const float* __restrict__ log
   int np = 128;
   while (np < (int)cnt) np <<= 1;
   for (int i = cnt + tid; i < np; i += 256) cand[i] = 0ull;
-  bitonic_desc(cand, np);
+  bitonic_desc_hybrid(cand, np);
   write_topk(cand, K, K, col_offset, io, vo);
 }
 
@@ -242,22 +308,23 @@ static int next_pow2(int v) {
   return p;
 }
 
-int launch_topk(const float* logits, int ld, int B, int N, int K, int col_offset, int32_t* idx, float* val,
-                cudaStream_t st) {
+int launch_topk(const float* logits, int ld, int B, int N, int K, int col_offset, long long out_stride, int32_t* idx,
+                float* val, cudaStream_t st) {
+  if (out_stride == 0) out_stride = K;
   EDGL_REQUIRE(K >= 1 && K <= 2048, "topk: K must be in [1,2048] (got %d)", K);
   EDGL_REQUIRE(N >= 1, "topk: N must be >= 1");
   if (B == 0) return 0;
   const int KP = next_pow2(K);
   const size_t smem = (size_t)(KP > kCandCap ? KP : kCandCap) * 8;
-  topk_kernel<<<B, 256, smem, st>>>(logits, ld, N, K, KP, col_offset, idx, val);
+  topk_kernel<<<B, 256, smem, st>>>(logits, ld, N, K, KP, col_offset, out_stride, idx, val);
   EDGL_LAUNCH_CHECK();
   return 0;
 }
 
-// merge: shard g's [Bt][K] block starts at cand_*[g * shard_stride]; entries with idx < 0 are padding.
+// merge: shard g's block starts at cand_*[g * shard_stride], its rows are row_stride apart; idx < 0 = padding.
 __global__ void __launch_bounds__(256) topk_merge_kernel(const float* __restrict__ cv, const int32_t* __restrict__ ci,
                                                          int G, int Bt, int K, int KP, long long shard_stride,
-                                                         int32_t* __restrict__ idx_out,
+                                                         long long row_stride, int32_t* __restrict__ idx_out,
                                                          float* __restrict__ val_out) {
   extern __shared__ __align__(16) unsigned long long cand[];
   const int row = blockIdx.x;
@@ -265,7 +332,7 @@ __global__ void __launch_bounds__(256) topk_merge_kernel(const float* __restrict
     unsigned long long c = 0ull;
     if (i < G * K) {
       const int g = i / K, j = i % K;
-      const long long o = (long long)g * shard_stride + (long long)row * K + j;
+      const long long o = (long long)g * shard_stride + (long long)row * row_stride + j;
       const int32_t id = ci[o];
       if (id >= 0) c = compose(f2key(cv[o]), (uint32_t)id);
     }
@@ -286,15 +353,16 @@ __global__ void __launch_bounds__(256) topk_merge_kernel(const float* __restrict
 }
 
 int launch_topk_merge(const float* cand_val, const int32_t* cand_idx, int G, int Bt, int K, long long shard_stride,
-                      int32_t* idx, float* val, cudaStream_t st) {
-  if (shard_stride == 0) shard_stride = (long long)Bt * K;
+                      long long row_stride, int32_t* idx, float* val, cudaStream_t st) {
+  if (row_stride == 0) row_stride = K;
+  if (shard_stride == 0) shard_stride = (long long)Bt * row_stride;
   EDGL_REQUIRE(G >= 1 && K >= 1 && (long long)G * K <= 16384, "topk_merge: G*K must be <= 16384");
   if (Bt == 0) return 0;
   const int KP = next_pow2(G * K);
   auto kern = topk_merge_kernel;
   const size_t smem = (size_t)KP * 8;
   if (smem > 48 * 1024) EDGL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<Bt, 256, smem, st>>>(cand_val, cand_idx, G, Bt, K, KP, shard_stride, idx, val);
+  kern<<<Bt, 256, smem, st>>>(cand_val, cand_idx, G, Bt, K, KP, shard_stride, row_stride, idx, val);
   EDGL_LAUNCH_CHECK();
   return 0;
 }

@@ -167,13 +167,24 @@ class Engine:
             check(self.lib.edgl_encode(self._handle, seqs_i.data_ptr(), seqs_t.data_ptr(), B, y.data_ptr(), _stream()))
         return y
 
-    def logits_topk(self, y, seen_ids=None, out=None):
-        """Local top-K of this handle's item shard for rows ``y`` [Bt,d]; global column ids."""
-        y = _req(y, torch.float32, "y", self.device)
+    def logits_topk(self, y, seen_ids=None, out=None, out_stride=0):
+        """Local top-K of this handle's item shard for rows ``y`` [Bt,d]; global column ids.
+        ``y`` / ``seen_ids`` may be row-strided views (e.g. columns of the packed exchange buffer);
+        ``out=(idx, val)`` may be views into one interleaved buffer with ``out_stride`` elements per row."""
+        def rows_view(t, dtype, name):
+            if not torch.is_tensor(t) or t.dtype != dtype or t.device != self.device or t.dim() != 2:
+                raise ValueError("%s must be a 2-D %s tensor on %s" % (name, dtype, self.device))
+            if t.stride(1) != 1:
+                t = t.contiguous()
+            return t, int(t.stride(0))
+        y, ys = rows_view(y, torch.float32, "y")
+        if ys % 4 != 0 or y.data_ptr() % 16 != 0:
+            y = y.contiguous()
+            ys = int(y.stride(0))
         Bt = int(y.shape[0])
-        seen_len = 0
+        seen_len, ss = 0, 0
         if seen_ids is not None:
-            seen_ids = _req(seen_ids, torch.int64, "seen_ids", self.device)
+            seen_ids, ss = rows_view(seen_ids, torch.int64, "seen_ids")
             seen_len = int(seen_ids.shape[1])
         if out is None:
             idx = torch.empty((Bt, self.K), dtype=torch.int32, device=self.device)
@@ -181,8 +192,8 @@ class Engine:
         else:
             idx, val = out
         with torch.cuda.device(self.device):
-            check(self.lib.edgl_logits_topk(self._handle, y.data_ptr(), _ptr(seen_ids), seen_len, Bt,
-                                            idx.data_ptr(), val.data_ptr(), _stream()))
+            check(self.lib.edgl_logits_topk(self._handle, y.data_ptr(), ys, _ptr(seen_ids), seen_len, ss, Bt,
+                                            out_stride, idx.data_ptr(), val.data_ptr(), _stream()))
         return idx, val
 
     # ------------------------------------------------------------------ layer-level
@@ -235,16 +246,17 @@ def topk_merge(cand_val: torch.Tensor, cand_idx: torch.Tensor):
     cand_val = _req(cand_val, torch.float32, "cand_val")
     cand_idx = _req(cand_idx, torch.int32, "cand_idx")
     G, Bt, K = cand_val.shape
-    return topk_merge_raw(cand_val.data_ptr(), cand_idx.data_ptr(), G, Bt, K, 0, cand_val.device)
+    return topk_merge_raw(cand_val.data_ptr(), cand_idx.data_ptr(), G, Bt, K, 0, 0, cand_val.device)
 
 
-def topk_merge_raw(val_ptr: int, idx_ptr: int, G: int, Bt: int, K: int, shard_stride: int, device):
-    """Merge with explicit base pointers / shard stride (used on the packed all-gather buffer)."""
+def topk_merge_raw(val_ptr: int, idx_ptr: int, G: int, Bt: int, K: int, shard_stride: int, row_stride: int, device):
+    """Merge with explicit base pointers / strides (used on the packed exchange buffer)."""
     lib = _lib.load()
     idx = torch.empty((Bt, K), dtype=torch.int32, device=device)
     val = torch.empty((Bt, K), dtype=torch.float32, device=device)
     with torch.cuda.device(device):
-        check(lib.edgl_topk_merge(val_ptr, idx_ptr, G, Bt, K, shard_stride, idx.data_ptr(), val.data_ptr(), _stream()))
+        check(lib.edgl_topk_merge(val_ptr, idx_ptr, G, Bt, K, shard_stride, row_stride, idx.data_ptr(), val.data_ptr(),
+                                  _stream()))
     return idx, val
 
 

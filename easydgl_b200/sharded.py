@@ -6,17 +6,20 @@ data-parallel with no exchange) and owns the item-table rows / logit columns
 
 1. all-gather of the packed rows ``[y (d fp32) | seqs_i (L int64, for the seen-mask)]``
    so that every rank can score every sequence against its column shard;
-2. all-gather of the per-shard top-K candidates ``(global idx int32, val fp32)`` - the
-   "single NCCL all-gather of per-shard top-K" of the north star - followed by a local
-   K-way merge (ties -> lower global id, Base.py:181) of this rank's own rows.
+2. exchange of the per-shard top-K candidates ``(global idx int32 | val fp32)`` (one interleaved
+   buffer), followed by a local K-way merge (ties -> lower global id, Base.py:181) of this
+   rank's own rows.  ``exchange="all_to_all"`` (default) sends every rank only the candidates of
+   ITS rows (1/G of the bytes); ``exchange="all_gather"`` is the literal "all-gather of per-shard
+   top-K" of the north star and leaves every rank holding every row's candidates.  Both produce
+   the same result.
 
 The reference has no multi-GPU path at all; parity is defined as: the merged
 top-K equals the single-GPU top-K bit for bit (tests/test_gpu_model.py,
-tests/test_sharded_gloo.py).
+tests/test_sharded_gloo.py, tools/check_sharded_nccl.py).
 
 ``torch.distributed`` is plumbing only.  ``engine`` is an ``easydgl_b200.engine.Engine``
 created with ``shard_rank=rank, shard_world=world``; the tests substitute a stand-in with
-the same four methods to exercise this file under gloo on CPU.
+the same methods to exercise this file under gloo on CPU.
 """
 from __future__ import annotations
 
@@ -32,11 +35,14 @@ def shard_bounds(num_rows: int, rank: int, world: int):
 
 
 class ShardedRanker:
-    def __init__(self, engine, group=None, merge_fn=None):
+    def __init__(self, engine, group=None, merge_fn=None, exchange="all_to_all"):
+        if exchange not in ("all_to_all", "all_gather"):
+            raise ValueError("exchange must be 'all_to_all' or 'all_gather'")
         self.engine = engine
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
+        self.exchange = exchange
         self.merge_fn = merge_fn if merge_fn is not None else _merge_packed_cuda
         self._bufs = {}
 
@@ -62,23 +68,29 @@ class ShardedRanker:
         mine[:, d:].copy_(seqs_i.contiguous().view(torch.float32))
         allp = self._buf("allpack", (G * B, W), torch.float32, dev)
         dist.all_gather_into_tensor(allp, mine, group=self.group)
-        y_all = allp[:, :d].contiguous()
-        seen_all = allp[:, d:].contiguous().view(torch.int64) if mask_seen else None
-        # ---- local: logits of ALL G*B rows against this rank's column shard + local top-K
-        cand = self._buf("cand", (2, G * B, K), torch.int32, dev)      # plane 0 = idx, plane 1 = val bits
-        eng.logits_topk(y_all, seen_all, out=(cand[0], cand[1].view(torch.float32)))
-        # ---- exchange 2: all-gather of the per-shard top-K
-        allc = self._buf("allcand", (G, 2, G * B, K), torch.int32, dev)
-        dist.all_gather_into_tensor(allc.view(G * 2, G * B, K), cand, group=self.group)  # concat along dim 0
-        # ---- merge this rank's rows [rank*B, (rank+1)*B) out of every shard's candidate block
+        # strided views into the gathered rows (no copies): y = first d floats, ids = the remaining 2L floats
+        y_all = allp[:, :d]
+        seen_all = allp.view(torch.int64)[:, d // 2:] if (mask_seen and d % 2 == 0) else (
+            allp[:, d:].contiguous().view(torch.int64) if mask_seen else None)
+        # ---- local: logits of ALL G*B rows against this rank's column shard + local top-K, written
+        #      interleaved: row r = [idx(K) | val bits(K)], rows of destination rank j are contiguous
+        cand = self._buf("cand", (G * B, 2, K), torch.int32, dev)
+        eng.logits_topk(y_all, seen_all, out=(cand[:, 0], cand[:, 1].view(torch.float32)), out_stride=2 * K)
+        # ---- exchange 2 + merge of this rank's rows
+        if self.exchange == "all_to_all":
+            recv = self._buf("recv", (G, B, 2, K), torch.int32, dev)       # recv[g] = shard g's candidates, my rows
+            dist.all_to_all_single(recv.view(G * B, 2, K), cand, group=self.group)
+            return self.merge_fn(recv, 0, B)
+        allc = self._buf("allcand", (G, G * B, 2, K), torch.int32, dev)    # allc[g] = all rows of shard g
+        dist.all_gather_into_tensor(allc.view(G * G * B, 2, K), cand, group=self.group)
         return self.merge_fn(allc, self.rank * B, B)
 
 
-def _merge_packed_cuda(allc: torch.Tensor, row0: int, B: int):
-    """allc int32 [G, 2, Bt, K] (plane 0 idx, plane 1 val bits) -> merged (idx, val) of rows row0..row0+B.
-    Shard g's block starts g * (2*Bt*K) elements after shard 0's: edgl_topk_merge's shard_stride."""
+def _merge_packed_cuda(buf: torch.Tensor, row0: int, B: int):
+    """buf int32 [G, rows, 2, K] (per row: idx | val bits) -> merged (idx, val) of rows row0..row0+B of every
+    shard.  Shard stride = rows*2K elements, row stride = 2K: edgl_topk_merge's strides."""
     from .engine import topk_merge_raw
-    G, _, Bt, K = allc.shape
-    idx_base = allc[0, 0, row0]
-    val_base = allc[0, 1, row0]
-    return topk_merge_raw(val_base.data_ptr(), idx_base.data_ptr(), G, B, K, 2 * Bt * K, allc.device)
+    G, rows, _, K = buf.shape
+    idx_base = buf[0, row0, 0]
+    val_base = buf[0, row0, 1]
+    return topk_merge_raw(val_base.data_ptr(), idx_base.data_ptr(), G, B, K, rows * 2 * K, 2 * K, buf.device)

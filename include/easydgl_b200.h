@@ -115,13 +115,18 @@ int edgl_forward_topk_host(edgl_handle* h, const int64_t* seqs_i_host, const flo
 /* Encoder up to y = hidden[:, -1]  [B,d]  (EasyDGL.py:69-146 / CTSMA.py:46-87). */
 int edgl_encode(edgl_handle* h, const int64_t* seqs_i, const float* seqs_t, int B, float* y, void* stream);
 /* y [Bt,d] x this handle's item-table shard -> logits + bias (EasyDGL.py:149-150), optional seen-mask
- * with seen_ids int64 [Bt,seen_len] (may be NULL), local top-K with GLOBAL column ids. */
-int edgl_logits_topk(edgl_handle* h, const float* y, const int64_t* seen_ids, int seen_len, int Bt,
-                     int32_t* cand_idx, float* cand_val, void* stream);
+ * with seen_ids int64 [Bt,seen_len] (may be NULL), local top-K with GLOBAL column ids.
+ * Strides are in elements, 0 = dense: row r of y starts at y[r*y_stride] (multiple of 4), of seen_ids at
+ * seen_ids[r*seen_stride], and its candidates are written at cand_*[r*cand_stride] - so the packed
+ * [y | ids] exchange rows and an interleaved [idx | val] buffer are used in place, without copies. */
+int edgl_logits_topk(edgl_handle* h, const float* y, int64_t y_stride, const int64_t* seen_ids, int seen_len,
+                     int64_t seen_stride, int Bt, int64_t cand_stride, int32_t* cand_idx, float* cand_val,
+                     void* stream);
 /* K-way merge of G per-shard candidate lists -> [Bt,K]; ties -> lower global index (Base.py:181).
- * Shard g's rows start at cand_*[g * shard_stride] (elements; 0 means dense [G,Bt,K]); idx < 0 = padding. */
+ * Shard g's block starts at cand_*[g * shard_stride], its rows are row_stride apart (elements; 0 means
+ * dense [G,Bt,K]); idx < 0 = padding. */
 int edgl_topk_merge(const float* cand_val, const int32_t* cand_idx, int G, int Bt, int K, int64_t shard_stride,
-                    int32_t* idx, float* val, void* stream);
+                    int64_t row_stride, int32_t* idx, float* val, void* stream);
 
 /* ---- layer-level entry points (one per reference layer, for unit parity) ---- */
 /* C.TimeSinusoidCoding(d).code(ts)  (coding.py:132-149): ts fp32 [B,L] already scaled -> [B,L,d]. */

@@ -129,6 +129,15 @@ def test_sharded_topk_equals_single(G):
         cv.append(v)
     mi, mv = engine.topk_merge(torch.stack(cv), torch.stack(ci))
     assert torch.equal(mi, gi) and torch.equal(mv, gv)
+    # the interleaved exchange layout ([rows, 2, K], strides 2K) used by easydgl_b200/sharded.py
+    K = single.K
+    buf = torch.empty((G, 10, 2, K), dtype=torch.int32, device=DEV)
+    for r in range(G):
+        sh = _engine(cfg, W, 10, shard_rank=r, shard_world=G)
+        sh.logits_topk(y, ids, out=(buf[r, :, 0], buf[r, :, 1].view(torch.float32)), out_stride=2 * K)
+    from easydgl_b200.sharded import _merge_packed_cuda
+    pi, pv = _merge_packed_cuda(buf, 0, 10)
+    assert torch.equal(pi, gi) and torch.equal(pv, gv)
 
 
 def test_host_entry_point_matches_device_entry_point():

@@ -35,7 +35,7 @@ class OracleShardEngine:
     def encode(self, ids, ts):
         return self.O.forward(ids, ts, self.W, self.cfg, dtype=torch.float64, return_all=True).y.float()
 
-    def logits_topk(self, y_all, seen_all, out):
+    def logits_topk(self, y_all, seen_all, out, out_stride=0):
         lg = y_all.double() @ self.table[self.c0:self.c1].t() + self.bias[self.c0:self.c1]
         if seen_all is not None:
             for b in range(lg.shape[0]):
@@ -47,11 +47,11 @@ class OracleShardEngine:
         out[1].copy_(v.float())
 
 
-def _cpu_merge(allc, row0, B):
-    G, _, Bt, K = allc.shape
-    idx = allc[:, 0, row0:row0 + B].permute(1, 0, 2).reshape(B, G * K).long()
-    val = allc[:, 1, row0:row0 + B].contiguous().view(torch.float32).permute(1, 0, 2).reshape(B, G * K).double()
-    key = -val * 1e6 + 0  # sort by (val desc, idx asc): stable sort on idx first, then on -val
+def _cpu_merge(buf, row0, B):
+    G, rows, _, K = buf.shape
+    idx = buf[:, row0:row0 + B, 0].permute(1, 0, 2).reshape(B, G * K).long()
+    val = buf[:, row0:row0 + B, 1].contiguous().view(torch.float32).permute(1, 0, 2).reshape(B, G * K).double()
+    # sort by (val desc, idx asc): stable sort on idx first, then on -val
     o1 = torch.sort(idx, dim=1, stable=True).indices
     idx, val = torch.gather(idx, 1, o1), torch.gather(val, 1, o1)
     o2 = torch.sort(-val, dim=1, stable=True).indices[:, :K]
@@ -73,13 +73,16 @@ def _worker(rank, world, port, q):
         W = synth.make_weights(cfg, mode="parity")
         inp = synth.make_inputs(cfg, 5, seed=100 + rank, edge_cases=False)
         eng = OracleShardEngine(cfg, W, rank, world, O)
-        ranker = ShardedRanker(eng, merge_fn=_cpu_merge)
+        ranker = ShardedRanker(eng, merge_fn=_cpu_merge, exchange="all_to_all")
         idx, val = ranker.forward_topk(inp["seqs_i"], inp["seqs_t"], mask_seen=True)
+        ranker_ag = ShardedRanker(eng, merge_fn=_cpu_merge, exchange="all_gather")
+        idx_ag, val_ag = ranker_ag.forward_topk(inp["seqs_i"], inp["seqs_t"], mask_seen=True)
         # single-device answer for this rank's rows
         full = OracleShardEngine(cfg, W, 0, 1, O)
         out = (torch.empty(5, 20, dtype=torch.int32), torch.empty(5, 20))
         full.logits_topk(full.encode(inp["seqs_i"], inp["seqs_t"]), inp["seqs_i"], out)
         ok = torch.equal(idx, out[0]) and torch.equal(val, out[1])
+        ok = ok and torch.equal(idx_ag, out[0]) and torch.equal(val_ag, out[1])
         # and without the seen-mask
         idx2, _ = ranker.forward_topk(inp["seqs_i"], inp["seqs_t"], mask_seen=False)
         full.logits_topk(full.encode(inp["seqs_i"], inp["seqs_t"]), None, out)

@@ -34,6 +34,8 @@ def main():
     shard = Engine(cfg, W, max_batch=B, device=dev, shard_rank=rank, shard_world=world)
     got_i, got_v = ShardedRanker(shard).forward_topk(ids, ts, True)
     ok = torch.equal(got_i, want_i) and torch.equal(got_v, want_v)
+    ag_i, ag_v = ShardedRanker(shard, exchange="all_gather").forward_topk(ids, ts, True)
+    ok = ok and torch.equal(ag_i, want_i) and torch.equal(ag_v, want_v)
     got_i2, _ = ShardedRanker(shard).forward_topk(ids, ts, False)
     want_i2, _ = single.forward_topk(ids, ts, False)
     ok = ok and torch.equal(got_i2, want_i2)

@@ -225,11 +225,16 @@ int launch_attention(const AttnArgs& a, cudaStream_t st) {
   if (a.B == 0) return 0;
   // tensor-core path (attn_mma.cuh) for the shapes it is instantiated for; EDGL_ATTN=simt forces the
   // CUDA-core kernel below (same results to fp32 rounding; used by the parity tests to cover both)
-  static const bool force_simt = [] {
+  static const char mode = [] {
     const char* e = getenv("EDGL_ATTN");
-    return e && e[0] == 's';
+    return e ? e[0] : 't';
   }();
-  if (!force_simt) {
+  const bool force_simt = mode == 's';
+  if (mode == 't') {  // tcgen05 / TMEM kernel (attn_tc.cu) for dh = 16, E = 16, L <= 128
+    const int r = launch_attention_tc(a, st);
+    if (r <= 0) return r;
+  }
+  if (!force_simt) {  // EDGL_ATTN=mma: the mma.sync kernel; EDGL_ATTN=simt: the CUDA-core kernel
     int r = 1;
     if (dh == 8) r = launch_attention_mma_dh8(a, st);
     else if (dh == 16) r = launch_attention_mma_dh16(a, st);

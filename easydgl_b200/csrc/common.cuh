@@ -106,6 +106,7 @@ struct AttnArgs {
   bool causal, diag_one;
 };
 int launch_attention(const AttnArgs& a, cudaStream_t st);
+int launch_attention_tc(const AttnArgs& a, cudaStream_t st);
 int launch_intensity(const float* H, const float* spans, const uint8_t* marks, const float* int_w,
                      const float* int_b, const float* int_weight, const float* int_scaling, int B, int L,
                      int h, int dh, int E, float* G, float* lam, cudaStream_t st);

@@ -227,10 +227,14 @@ int launch_attention(const AttnArgs& a, cudaStream_t st) {
   // CUDA-core kernel below (same results to fp32 rounding; used by the parity tests to cover both)
   static const char mode = [] {
     const char* e = getenv("EDGL_ATTN");
-    return e ? e[0] : 't';
+    return e ? e[0] : 'm';
   }();
   const bool force_simt = mode == 's';
-  if (mode == 't') {  // tcgen05 / TMEM kernel (attn_tc.cu) for dh = 16, E = 16, L <= 128
+  // EDGL_ATTN=tc: the tcgen05 / TMEM kernel (attn_tc.cu; dh = 16, E = 16, L <= 128).  It passes the same
+  // parity tests but its phases are serialised per (sequence, head) item - one item fills the 512 TMEM
+  // columns - so it is slower (3.4 ms vs 2.1 ms at C2) than the register-resident mma.sync kernel, which
+  // stays the default until the TMEM budget allows two items in flight.
+  if (mode == 't') {
     const int r = launch_attention_tc(a, st);
     if (r <= 0) return r;
   }

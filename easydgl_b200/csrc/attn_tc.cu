@@ -18,6 +18,7 @@
 // descriptors of gemm_tc.cu use (rows of 128 B, 16-byte chunk c of row r stored at chunk c ^ (r & 7)).
 // W1' = -log2(e) * [W1 ; w_span ; b1] so the MMA yields -z*log2(e) and sigmoid = rcp(1 + ex2(.)).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -149,7 +150,7 @@ __device__ __forceinline__ void put4(uint8_t* th, uint8_t* tl, int r, int k, flo
 
 enum { B_STAGED = 0, B_S, B_P, B_HU, B_A, B_Z0, B_Z1, B_ZF0, B_ZF1, B_L, B_G, B_GP, B_O, B_COUNT };
 
-__global__ void __launch_bounds__(160, 1) attention_tc_kernel(AttnArgs a, int num_items) {
+__global__ void __launch_bounds__(160, 1) attention_tc_kernel(AttnArgs a, int num_items, long long* dbg) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bar = reinterpret_cast<uint64_t*>(sm + OFF_BAR);
@@ -270,11 +271,14 @@ __global__ void __launch_bounds__(160, 1) attention_tc_kernel(AttnArgs a, int nu
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
     const bool row_ok = r < L;
     const float sc2 = kLog2e / sqrtf((float)DH);
+    long long dacc[12] = {0};
     uint32_t n = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++n) {
       const uint32_t ph = n & 1;
       const int b = item / a.h, hh = item % a.h;
       const long long grow = (long long)b * L + (row_ok ? r : L - 1);
+      long long tq = clock64(), tn;
+#define EDGL_T(i) tn = clock64(); dacc[i] += tn - tq; tq = tn;
       // ---------------- stage this row's operands (rows >= L are zero / masked)
       {
         float4 q4[4], k4[4], t4[4], v4[4];
@@ -322,8 +326,10 @@ __global__ void __launch_bounds__(160, 1) attention_tc_kernel(AttnArgs a, int nu
       mbar_arrive(&bar[B_STAGED]);
       asm volatile("bar.sync 1, 128;" ::: "memory");  // km[] is read by the other row threads below
 
+      EDGL_T(0)
       // ---------------- softmax over the S row (two passes over TMEM: max, then exp / sum / store)
       mbar_wait(&bar[B_S], ph);
+      EDGL_T(1)
       tc_fence_after();
       float m = -INFINITY;
       for (int c = 0; c < NS; c += 16) {
@@ -357,9 +363,11 @@ __global__ void __launch_bounds__(160, 1) attention_tc_kernel(AttnArgs a, int nu
       tc_fence_before();
       mbar_arrive(&bar[B_P]);
       const float inv_l = __frcp_rn(l);
+      EDGL_T(2)
 
       // ---------------- H = Hu / l ; A operand of the MLP = [H (16) | span | 1 | 0 x 6]
       mbar_wait(&bar[B_HU], ph);
+      EDGL_T(3)
       tc_fence_after();
       {
         float hu[16];
@@ -383,6 +391,7 @@ __global__ void __launch_bounds__(160, 1) attention_tc_kernel(AttnArgs a, int nu
       }
       tc_fence_before();
       mbar_arrive(&bar[B_A]);
+      EDGL_T(4)
 
       // ---------------- sigmoid-dot epilogue of the MLP quarters -> per-event pre-activations
       float ls[E];
@@ -393,6 +402,7 @@ __global__ void __launch_bounds__(160, 1) attention_tc_kernel(AttnArgs a, int nu
         const int buf = qz & 1;
         const uint32_t use = 2 * n + (qz >> 1);
         mbar_wait(&bar[B_Z0 + buf], use & 1);
+        EDGL_T(5)
         tc_fence_after();
 #pragma unroll
         for (int ev = 0; ev < 4; ++ev) {  // one event = 16 columns
@@ -412,6 +422,7 @@ __global__ void __launch_bounds__(160, 1) attention_tc_kernel(AttnArgs a, int nu
         }
         tc_fence_before();
         mbar_arrive(&bar[B_ZF0 + buf]);
+        EDGL_T(6)
       }
       // ---------------- lam_e = s_e ln(1 + exp(x / s_e))   (temporal.py:305-306, naive softplus, Q6)
       {
@@ -436,9 +447,11 @@ __global__ void __launch_bounds__(160, 1) attention_tc_kernel(AttnArgs a, int nu
       }
       tc_fence_before();
       mbar_arrive(&bar[B_L]);
+      EDGL_T(7)
 
       // ---------------- gate: P <- G o P  (set_diag for BiMAU), temporal.py:438-441
       mbar_wait(&bar[B_G], ph);
+      EDGL_T(8)
       tc_fence_after();
       for (int c = 0; c < NS; c += 16) {
         float g[16], p[16];
@@ -458,9 +471,11 @@ __global__ void __launch_bounds__(160, 1) attention_tc_kernel(AttnArgs a, int nu
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&bar[B_GP]);
+      EDGL_T(9)
 
       // ---------------- O = Ou / l + residual   (temporal.py:385,447)
       mbar_wait(&bar[B_O], ph);
+      EDGL_T(10)
       tc_fence_after();
       {
         float o[16];
@@ -480,7 +495,9 @@ __global__ void __launch_bounds__(160, 1) attention_tc_kernel(AttnArgs a, int nu
         }
       }
       tc_fence_before();  // TMEM reads of this item are done before the next item's operands / MMAs
+      EDGL_T(11)
     }
+    if (dbg && tid == 0 && blockIdx.x == 0) for (int i = 0; i < 12; ++i) dbg[i] = dacc[i];
   }
   tc_fence_before();
   __syncthreads();
@@ -509,8 +526,22 @@ int launch_attention_tc(const AttnArgs& a, cudaStream_t st) {
   auto kern = attention_tc_kernel;
   EDGL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   const int grid = items < num_sms ? (int)items : num_sms;
-  kern<<<grid, 160, SMEM_BYTES, st>>>(a, (int)items);
+  static const bool debug = getenv("EDGL_TC_DEBUG") != nullptr;
+  static long long* dbg = nullptr;
+  if (debug && !dbg) cudaMalloc(&dbg, 16 * sizeof(long long));
+  kern<<<grid, 160, SMEM_BYTES, st>>>(a, (int)items, debug ? dbg : nullptr);
   EDGL_LAUNCH_CHECK();
+  if (debug) {
+    long long h[12];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
+    const double it = (double)((items + grid - 1) / grid);
+    const char* nm[12] = {"stage", "wait_S", "softmax", "wait_HU", "H->A", "wait_Z", "sigmoid", "lambda", "wait_G", "gate",
+                          "wait_O", "out"};
+    fprintf(stderr, "[attn_tc] cycles/item (CTA 0, row thread 0):");
+    for (int i = 0; i < 12; ++i) fprintf(stderr, " %s %.0f |", nm[i], h[i] / it);
+    fprintf(stderr, "\n");
+  }
   return 0;
 }
 

@@ -383,7 +383,7 @@ def _main(out_fd):
     ap.add_argument("--batch", type=int, default=0, help="override per-GPU batch (debug only)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-steps", type=int, default=20)
-    ap.add_argument("--exchange", default="all_to_all", choices=["all_to_all", "all_gather"],
+    ap.add_argument("--exchange", default="all_to_all", choices=["all_to_all", "all_gather", "p2p"],
                     help="candidate exchange of the column-sharded multi-GPU path")
     args = ap.parse_args()
     args.out_fd = out_fd

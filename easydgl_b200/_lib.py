@@ -44,6 +44,13 @@ _SIGS = {
     "edgl_forward_topk_host": (_I, [_P, _P, _P, _I, _I, _P, _P, _P]),
     "edgl_encode": (_I, [_P, _P, _P, _I, _P, _P]),
     "edgl_logits_topk": (_I, [_P, _P, C.c_int64, _P, _I, C.c_int64, _I, C.c_int64, _P, _P, _P]),
+    "edgl_xchg_alloc": (_I, [C.c_int64, C.POINTER(_P), _P]),
+    "edgl_xchg_open": (_I, [_P, C.POINTER(_P)]),
+    "edgl_xchg_close": (_I, [_P]),
+    "edgl_xchg_free": (_I, [_P]),
+    "edgl_xchg_put_rows": (_I, [_P, _P, C.c_int64, _P, _I, _P, _P, _I, _I, C.c_uint32, _P]),
+    "edgl_xchg_wait": (_I, [_P, _I, C.c_uint32, _P]),
+    "edgl_logits_topk_p2p": (_I, [_P, _P, C.c_int64, _P, _I, C.c_int64, _I, _I, _P, _P, _I, _I, C.c_uint32, _P]),
     "edgl_topk_merge": (_I, [_P, _P, _I, _I, _I, C.c_int64, C.c_int64, _P, _P, _P]),
     "edgl_time_sinusoid_code": (_I, [_P, _I, _I, _I, _P, _P]),
     "edgl_embedding_lookup": (_I, [_P, _I, _I, _I, _I, _P, C.c_int64, _P, _P]),

@@ -62,6 +62,7 @@ struct edgl_handle {
   float* tscale = nullptr;
   uint8_t* mark8 = nullptr;
   int* flag = nullptr;
+  unsigned int* p2p_counter = nullptr;  // grid-done counters of the fused-exchange kernels (zero-initialised)
   float* bias_full = nullptr;  // [N1] = concat([-1000], output_bias)  (Base.py:110)
   float* wfold0 = nullptr;     // EasyDGL block 0: [Ka,4d]
   float* pbias0 = nullptr;     // EasyDGL block 0: [L,4d] = pos_embs @ W[d:2d] + b
@@ -326,7 +327,8 @@ int logits_rows(edgl_handle* h, const float* y, int ldy, long long rc, float* ou
 }
 
 int logits_topk(edgl_handle* h, const float* y, int ldy, const int64_t* seen, int seen_len, long long seen_stride,
-                long long Bt, int32_t* idx, float* val, long long ostride, cudaStream_t st) {
+                long long Bt, int32_t* idx, float* val, long long ostride, cudaStream_t st,
+                const TopkP2P* p2p = nullptr) {
   if (ostride == 0) ostride = h->K;
   if (ldy == 0) ldy = h->d;
   if (seen_stride == 0) seen_stride = seen_len;
@@ -341,7 +343,15 @@ int logits_topk(edgl_handle* h, const float* y, int ldy, const int64_t* seen, in
       EDGL_TRY(launch_mask_seen(h->logits_ws, ldw, (int)rc, seen + r0 * seen_stride, seen_len, seen_stride, h->c0, h->c1, st));
     }
     mark(h, ST_TOPK, st);
-    EDGL_TRY(launch_topk(h->logits_ws, ldw, (int)rc, Ns, h->K, (int)h->c0, ostride, idx + r0 * ostride, val + r0 * ostride, st));
+    if (p2p) {
+      TopkP2P pp = *p2p;
+      pp.row_base = (int)r0;
+      pp.signal = (r0 + rc >= Bt) ? 1 : 0;  // raise the peers' flags after the last chunk only
+      EDGL_TRY(launch_topk(h->logits_ws, ldw, (int)rc, Ns, h->K, (int)h->c0, 0, nullptr, nullptr, st, &pp));
+    } else {
+      EDGL_TRY(launch_topk(h->logits_ws, ldw, (int)rc, Ns, h->K, (int)h->c0, ostride, idx + r0 * ostride,
+                           val + r0 * ostride, st));
+    }
   }
   mark(h, ST_END, st);
   return 0;
@@ -401,6 +411,8 @@ int edgl_create(const edgl_config* cfg, edgl_handle** out) {
   EDGL_ALLOC(h->tscale, d / 2);
   EDGL_ALLOC(h->mark8, (long long)cfg->mark_rows * h->E);
   EDGL_ALLOC(h->flag, 1);
+  EDGL_ALLOC(h->p2p_counter, 4);
+  if (!rc && cudaMemset(h->p2p_counter, 0, 4 * sizeof(unsigned int)) != cudaSuccess) rc = set_error(EDGL_ECUDA, "cudaMemset failed");
   EDGL_ALLOC(h->bias_full, h->N1);
   if (easy) {
     EDGL_ALLOC(h->wfold0, (long long)h->Ka * 4 * d);
@@ -663,6 +675,73 @@ int edgl_logits_topk(edgl_handle* h, const float* y, int64_t y_stride, const int
   EDGL_REQUIRE(seen_stride == 0 || seen_stride >= seen_len, "seen_stride must be 0 or >= seen_len");
   return logits_topk(h, y, (int)y_stride, seen_ids, seen_len, seen_stride, Bt, cand_idx, cand_val, cand_stride,
                      (cudaStream_t)stream);
+}
+
+/* ---- fused exchange over peer memory (CUDA IPC + NVLink P2P stores) ---- */
+int edgl_xchg_alloc(int64_t bytes, void** dev_ptr, void* ipc_handle_out) {
+  if (!dev_ptr || !ipc_handle_out || bytes <= 0) return set_error(EDGL_EINVAL, "bad argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  void* p = nullptr;
+  EDGL_CUDA(cudaMalloc(&p, (size_t)bytes));
+  EDGL_CUDA(cudaMemset(p, 0, (size_t)bytes));
+  cudaIpcMemHandle_t hd;
+  EDGL_CUDA(cudaIpcGetMemHandle(&hd, p));
+  memcpy(ipc_handle_out, &hd, sizeof(hd));
+  *dev_ptr = p;
+  return 0;
+}
+
+int edgl_xchg_open(const void* ipc_handle, void** dev_ptr) {
+  if (!ipc_handle || !dev_ptr) return set_error(EDGL_EINVAL, "null argument");
+  cudaIpcMemHandle_t hd;
+  memcpy(&hd, ipc_handle, sizeof(hd));
+  EDGL_CUDA(cudaIpcOpenMemHandle(dev_ptr, hd, cudaIpcMemLazyEnablePeerAccess));
+  return 0;
+}
+
+int edgl_xchg_close(void* dev_ptr) {
+  if (dev_ptr) EDGL_CUDA(cudaIpcCloseMemHandle(dev_ptr));
+  return 0;
+}
+
+int edgl_xchg_free(void* dev_ptr) {
+  if (dev_ptr) EDGL_CUDA(cudaFree(dev_ptr));
+  return 0;
+}
+
+int edgl_xchg_put_rows(edgl_handle* h, const float* y, int64_t y_stride, const int64_t* seqs_i, int B,
+                       const int64_t* peer_rows, const int64_t* peer_flags, int G, int rank, uint32_t epoch,
+                       void* stream) {
+  EDGL_TRY(check_ready(h, B));
+  if (!y || !seqs_i || !peer_rows || !peer_flags) return set_error(EDGL_EINVAL, "null argument");
+  EDGL_REQUIRE(G >= 1 && G <= 32 && rank >= 0 && rank < G, "bad G/rank");
+  if (y_stride == 0) y_stride = h->d;
+  return launch_put_rows(y, y_stride, seqs_i, h->L, h->d, B, reinterpret_cast<const long long*>(peer_rows), G, rank,
+                         reinterpret_cast<const long long*>(peer_flags), epoch, h->p2p_counter, (cudaStream_t)stream);
+}
+
+int edgl_xchg_wait(const uint32_t* flags, int G, uint32_t epoch, void* stream) {
+  if (!flags) return set_error(EDGL_EINVAL, "null argument");
+  EDGL_REQUIRE(G >= 1 && G <= 32, "bad G");
+  return launch_wait_flags(flags, G, epoch, (cudaStream_t)stream);
+}
+
+int edgl_logits_topk_p2p(edgl_handle* h, const float* y, int64_t y_stride, const int64_t* seen_ids, int seen_len,
+                         int64_t seen_stride, int Bt, int rows_per_dest, const int64_t* peer_cand,
+                         const int64_t* peer_flags, int G, int rank, uint32_t epoch, void* stream) {
+  EDGL_TRY(check_ready(h, Bt, false));
+  if (!y || !peer_cand || !peer_flags) return set_error(EDGL_EINVAL, "null argument");
+  EDGL_REQUIRE(G >= 1 && G <= 32 && rank >= 0 && rank < G && rows_per_dest >= 1 && Bt == G * rows_per_dest,
+               "bad G/rank/rows_per_dest");
+  EDGL_REQUIRE(y_stride == 0 || (y_stride >= h->d && y_stride % 4 == 0), "y_stride must be 0 or a multiple of 4 >= d");
+  TopkP2P pp;
+  memset(&pp, 0, sizeof(pp));
+  pp.dest = reinterpret_cast<const long long*>(peer_cand);
+  pp.peer_flags = reinterpret_cast<const long long*>(peer_flags);
+  pp.counter = h->p2p_counter + 1;
+  pp.rows_per_dest = rows_per_dest; pp.my_rank = rank; pp.G = G; pp.epoch = epoch;
+  return logits_topk(h, y, (int)y_stride, seen_ids, seen_len, seen_stride, Bt, nullptr, nullptr, 0,
+                     (cudaStream_t)stream, &pp);
 }
 
 int edgl_topk_merge(const float* cand_val, const int32_t* cand_idx, int G, int Bt, int K, int64_t shard_stride,

@@ -117,8 +117,22 @@ int launch_layernorm(const float* x, const float* gamma, const float* beta, int 
 
 int launch_mask_seen(float* logits, int ld, int B, const int64_t* ids, int seen_len, long long seen_stride,
                      long long col0, long long col1, cudaStream_t st);
+// Fused candidate exchange over peer memory (multi-GPU): when `dest` is set the top-K kernel writes row R's
+// candidates into the receive buffer of rank R / rows_per_dest and, after the last launch of a step, raises
+// `epoch` in every peer's flag array.
+struct TopkP2P {
+  const long long* dest;        // device array [G]: base address of each rank's candidate buffer [G][B][2][K] int32
+  const long long* peer_flags;  // device array [G]: address of each rank's uint32 flag array [G]
+  unsigned int* counter;        // device scratch (grid-done counter), zero-initialised
+  int rows_per_dest, my_rank, row_base, G, signal;
+  uint32_t epoch;
+};
 int launch_topk(const float* logits, int ld, int B, int N, int K, int col_offset, long long out_stride, int32_t* idx,
-                float* val, cudaStream_t st);
+                float* val, cudaStream_t st, const TopkP2P* p2p = nullptr);
+int launch_put_rows(const float* y, long long ldy, const int64_t* ids, int L, int d, int B, const long long* peer_rows,
+                    int G, int rank, const long long* peer_flags, uint32_t epoch, unsigned int* counter,
+                    cudaStream_t st);
+int launch_wait_flags(const uint32_t* flags, int G, uint32_t epoch, cudaStream_t st);
 int launch_topk_merge(const float* cand_val, const int32_t* cand_idx, int G, int Bt, int K, long long shard_stride,
                       long long row_stride, int32_t* idx, float* val, cudaStream_t st);
 

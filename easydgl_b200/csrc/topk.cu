@@ -5,6 +5,8 @@
 // Ranking is done on the masked logits: softmax (Base.py:164) is monotone, so the order is the same
 // wherever fp32 softmax is injective (DESIGN.md discusses the underflow corner).
 // Integer/index work: bit-exact by construction (order-preserving uint keys, radix select, ties by index).
+#include <string.h>
+
 #include "common.cuh"
 
 namespace edgl {
@@ -228,21 +230,69 @@ __device__ void topk_row_radix(const float* __restrict__ p, int N, int K, int KP
 // buffer (constant rows, everything masked) take the radix path.  Two coalesced reads of the row.
 constexpr int kCandCap = 1024;
 
+// system-scope release store / acquire load for the cross-GPU flags (peer memory over NVLink)
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Called by every thread of every CTA after its last peer write: the last CTA of the grid publishes
+// `epoch` into slot `my_rank` of every peer's flag array (the writes of all CTAs are fenced before it).
+__device__ void p2p_signal_when_grid_done(unsigned int* counter, const long long* peer_flags, int G, int my_rank,
+                                          uint32_t epoch) {
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int prev = atomicAdd(counter, 1u);
+    if (prev == gridDim.x - 1) {
+      *counter = 0;
+      __threadfence_system();
+      for (int g = 0; g < G; ++g) st_release_sys(reinterpret_cast<uint32_t*>(peer_flags[g]) + my_rank, epoch);
+    }
+  }
+}
+
+__device__ void topk_row(const float* __restrict__ p, int ld_vec_ok, int N, int K, int KP, int col_offset,
+                         unsigned long long* cand, int32_t* __restrict__ io, float* __restrict__ vo);
+
 __global__ void __launch_bounds__(256) topk_kernel(const float* __restrict__ logits, int ld, int N, int K, int KP,
                                                    int col_offset, long long out_stride,
-                                                   int32_t* __restrict__ idx_out, float* __restrict__ val_out) {
+                                                   int32_t* __restrict__ idx_out, float* __restrict__ val_out,
+                                                   TopkP2P pp) {
   extern __shared__ __align__(16) unsigned long long cand[];  // max(KP, kCandCap) entries
+  const float* p = logits + (long long)blockIdx.x * ld;
+  int32_t* io;
+  float* vo;
+  if (pp.dest) {
+    // fused exchange: row R of the gathered batch belongs to rank R / rows_per_dest; its candidates go
+    // straight into that rank's receive buffer (block my_rank, interleaved [idx | val]) over NVLink
+    const long long R = (long long)pp.row_base + blockIdx.x;
+    const int dst = (int)(R / pp.rows_per_dest);
+    io = reinterpret_cast<int32_t*>(pp.dest[dst]) +
+         ((long long)pp.my_rank * pp.rows_per_dest + (R - (long long)dst * pp.rows_per_dest)) * (2 * K);
+    vo = reinterpret_cast<float*>(io + K);
+  } else {
+    io = idx_out + (long long)blockIdx.x * out_stride;
+    vo = val_out + (long long)blockIdx.x * out_stride;
+  }
+  const int vec = (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(logits) & 15) == 0);
+  topk_row(p, vec, N, K, KP, col_offset, cand, io, vo);
+  if (pp.dest && pp.signal) p2p_signal_when_grid_done(pp.counter, pp.peer_flags, pp.G, pp.my_rank, pp.epoch);
+}
+
+__device__ void topk_row(const float* __restrict__ p, int vec, int N, int K, int KP, int col_offset,
+                         unsigned long long* cand, int32_t* __restrict__ io, float* __restrict__ vo) {
   __shared__ unsigned int s_cnt;
   __shared__ uint32_t s_t0, s_wt[8];
-  const float* p = logits + (long long)blockIdx.x * ld;
-  int32_t* io = idx_out + (long long)blockIdx.x * out_stride;
-  float* vo = val_out + (long long)blockIdx.x * out_stride;
   const int tid = threadIdx.x;
   if (K > 256 || N < 1024) {
     topk_row_radix(p, N, K, KP, col_offset, cand, io, vo);
     return;
   }
-  const bool vec = (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(logits) & 15) == 0);
   const int N4 = vec ? (N >> 2) : 0;
   // ---- pass 1: slice maxima
   uint32_t mx = 0;
@@ -309,14 +359,17 @@ static int next_pow2(int v) {
 }
 
 int launch_topk(const float* logits, int ld, int B, int N, int K, int col_offset, long long out_stride, int32_t* idx,
-                float* val, cudaStream_t st) {
+                float* val, cudaStream_t st, const TopkP2P* p2p) {
   if (out_stride == 0) out_stride = K;
+  TopkP2P pp;
+  memset(&pp, 0, sizeof(pp));
+  if (p2p) pp = *p2p;
   EDGL_REQUIRE(K >= 1 && K <= 2048, "topk: K must be in [1,2048] (got %d)", K);
   EDGL_REQUIRE(N >= 1, "topk: N must be >= 1");
   if (B == 0) return 0;
   const int KP = next_pow2(K);
   const size_t smem = (size_t)(KP > kCandCap ? KP : kCandCap) * 8;
-  topk_kernel<<<B, 256, smem, st>>>(logits, ld, N, K, KP, col_offset, out_stride, idx, val);
+  topk_kernel<<<B, 256, smem, st>>>(logits, ld, N, K, KP, col_offset, out_stride, idx, val, pp);
   EDGL_LAUNCH_CHECK();
   return 0;
 }
@@ -363,6 +416,45 @@ int launch_topk_merge(const float* cand_val, const int32_t* cand_idx, int G, int
   const size_t smem = (size_t)KP * 8;
   if (smem > 48 * 1024) EDGL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<Bt, 256, smem, st>>>(cand_val, cand_idx, G, Bt, K, KP, shard_stride, row_stride, idx, val);
+  EDGL_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---- fused exchange 1: packed [y | seqs_i] rows of this rank -> slot `rank` of EVERY peer's gathered buffer
+__global__ void __launch_bounds__(256) put_rows_kernel(const float* __restrict__ y, long long ldy,
+                                                       const int64_t* __restrict__ ids, int L, int d, int B,
+                                                       const long long* __restrict__ peer_rows, int G, int rank,
+                                                       const long long* __restrict__ peer_flags, uint32_t epoch,
+                                                       unsigned int* counter) {
+  const int b = blockIdx.x;
+  const int W = d + 2 * L;
+  const float* idf = reinterpret_cast<const float*>(ids + (long long)b * L);  // raw bytes of the int64 ids
+  for (int t = threadIdx.x; t < W; t += blockDim.x) {
+    const float v = t < d ? y[b * ldy + t] : idf[t - d];
+    const long long off = ((long long)rank * B + b) * W + t;
+    for (int g = 0; g < G; ++g) reinterpret_cast<float*>(peer_rows[g])[off] = v;
+  }
+  p2p_signal_when_grid_done(counter, peer_flags, G, rank, epoch);
+}
+
+int launch_put_rows(const float* y, long long ldy, const int64_t* ids, int L, int d, int B, const long long* peer_rows,
+                    int G, int rank, const long long* peer_flags, uint32_t epoch, unsigned int* counter,
+                    cudaStream_t st) {
+  if (B == 0) return 0;
+  put_rows_kernel<<<B, 256, 0, st>>>(y, ldy, ids, L, d, B, peer_rows, G, rank, peer_flags, epoch, counter);
+  EDGL_LAUNCH_CHECK();
+  return 0;
+}
+
+// spin until every one of the G flags has reached `epoch` (wrap-around safe)
+__global__ void wait_flags_kernel(const uint32_t* flags, int G, uint32_t epoch) {
+  const int g = threadIdx.x;
+  if (g < G)
+    while ((int)(ld_acquire_sys(flags + g) - epoch) < 0) __nanosleep(64);
+}
+
+int launch_wait_flags(const uint32_t* flags, int G, uint32_t epoch, cudaStream_t st) {
+  wait_flags_kernel<<<1, 32, 0, st>>>(flags, G, epoch);
   EDGL_LAUNCH_CHECK();
   return 0;
 }

@@ -10,8 +10,11 @@ data-parallel with no exchange) and owns the item-table rows / logit columns
    buffer), followed by a local K-way merge (ties -> lower global id, Base.py:181) of this
    rank's own rows.  ``exchange="all_to_all"`` (default) sends every rank only the candidates of
    ITS rows (1/G of the bytes); ``exchange="all_gather"`` is the literal "all-gather of per-shard
-   top-K" of the north star and leaves every rank holding every row's candidates.  Both produce
-   the same result.
+   top-K" of the north star and leaves every rank holding every row's candidates.
+   ``exchange="p2p"`` fuses BOTH exchanges into the kernels: the packed rows and the top-K
+   candidates are written straight into the peers' memory over NVLink (CUDA-IPC-mapped buffers,
+   system-scope release/acquire flags) by ``edgl_xchg_put_rows`` and by the top-K kernel itself
+   (``edgl_logits_topk_p2p``); no NCCL call remains on the data path.  All three give the same result.
 
 The reference has no multi-GPU path at all; parity is defined as: the merged
 top-K equals the single-GPU top-K bit for bit (tests/test_gpu_model.py,
@@ -36,8 +39,8 @@ def shard_bounds(num_rows: int, rank: int, world: int):
 
 class ShardedRanker:
     def __init__(self, engine, group=None, merge_fn=None, exchange="all_to_all"):
-        if exchange not in ("all_to_all", "all_gather"):
-            raise ValueError("exchange must be 'all_to_all' or 'all_gather'")
+        if exchange not in ("all_to_all", "all_gather", "p2p"):
+            raise ValueError("exchange must be 'all_to_all', 'all_gather' or 'p2p'")
         self.engine = engine
         self.group = group
         self.world = dist.get_world_size(group)
@@ -45,6 +48,7 @@ class ShardedRanker:
         self.exchange = exchange
         self.merge_fn = merge_fn if merge_fn is not None else _merge_packed_cuda
         self._bufs = {}
+        self._peer = None
 
     def _buf(self, name, shape, dtype, device):
         key = (name, tuple(shape), dtype, str(device))
@@ -60,6 +64,10 @@ class ShardedRanker:
         B, L = seqs_i.shape
         d, K = eng.d, eng.K
         dev = seqs_i.device
+        if self.exchange == "p2p":
+            if self._peer is None or self._peer.B != B:
+                self._peer = PeerExchange(eng, B, self.group)
+            return self._peer.forward_topk(seqs_i, seqs_t, mask_seen)
         # ---- exchange 1: packed [y | ids] rows (ids travel as raw bytes in fp32 lanes)
         y = eng.encode(seqs_i, seqs_t)
         W = d + 2 * L
@@ -94,3 +102,80 @@ def _merge_packed_cuda(buf: torch.Tensor, row0: int, B: int):
     idx_base = buf[0, row0, 0]
     val_base = buf[0, row0, 1]
     return topk_merge_raw(val_base.data_ptr(), idx_base.data_ptr(), G, B, K, rows * 2 * K, 2 * K, buf.device)
+
+
+class PeerExchange:
+    """Peer-memory exchange region of one rank + the mapped regions of its peers (see include/easydgl_b200.h,
+    "fused exchange over peer memory").  NCCL is used once, at construction, to ship the 64-byte IPC handles."""
+
+    def __init__(self, engine, B: int, group=None):
+        import ctypes as C
+        from ._lib import check
+        self.eng, self.lib, self.B, self.group = engine, engine.lib, int(B), group
+        self.G, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        G, d, L, K = self.G, engine.d, engine.L, engine.K
+        self.W = d + 2 * L
+        if self.W % 4 or d % 4:
+            raise ValueError("p2p exchange needs d and d + 2L to be multiples of 4")
+        self.off_rows = 0
+        self.off_cand = self.off_rows + G * B * self.W * 4
+        self.off_frows = (self.off_cand + G * B * 2 * K * 4 + 255) // 256 * 256
+        self.off_fcand = self.off_frows + 256
+        total = self.off_fcand + 256
+        dev = engine.device
+        with torch.cuda.device(dev):
+            ptr = C.c_void_p()
+            handle = (C.c_ubyte * 64)()
+            check(self.lib.edgl_xchg_alloc(total, C.byref(ptr), handle))
+            self.base = ptr.value
+            mine = torch.tensor(list(bytes(handle)), dtype=torch.uint8, device=dev)
+            allh = torch.empty((G, 64), dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(allh.view(-1), mine, group=group)
+            allh = allh.cpu()
+            self.peers, self._opened = [], []
+            for g in range(G):
+                if g == self.rank:
+                    self.peers.append(self.base)
+                    continue
+                hb = (C.c_ubyte * 64).from_buffer_copy(bytes(allh[g].tolist()))
+                pp = C.c_void_p()
+                check(self.lib.edgl_xchg_open(hb, C.byref(pp)))
+                self.peers.append(pp.value)
+                self._opened.append(pp.value)
+
+            def table(off):
+                return torch.tensor([p + off for p in self.peers], dtype=torch.int64, device=dev)
+            self.t_rows, self.t_cand = table(self.off_rows), table(self.off_cand)
+            self.t_frows, self.t_fcand = table(self.off_frows), table(self.off_fcand)
+        self.epoch = 0
+        dist.barrier(group=group)
+
+    def forward_topk(self, seqs_i, seqs_t, mask_seen=True):
+        from ._lib import check
+        from .engine import _stream, topk_merge_raw
+        eng, lib, G, B, K, W, d, L = self.eng, self.lib, self.G, self.B, self.eng.K, self.W, self.eng.d, self.eng.L
+        self.epoch += 1
+        e = self.epoch
+        seqs_i = seqs_i.contiguous()
+        y = eng.encode(seqs_i, seqs_t)
+        h = eng._handle
+        with torch.cuda.device(eng.device):
+            st = _stream()
+            check(lib.edgl_xchg_put_rows(h, y.data_ptr(), 0, seqs_i.data_ptr(), B, self.t_rows.data_ptr(),
+                                         self.t_frows.data_ptr(), G, self.rank, e, st))
+            check(lib.edgl_xchg_wait(self.base + self.off_frows, G, e, st))
+            rows = self.base + self.off_rows
+            seen = rows + d * 4 if mask_seen else None
+            check(lib.edgl_logits_topk_p2p(h, rows, W, seen, L, W // 2, G * B, B, self.t_cand.data_ptr(),
+                                           self.t_fcand.data_ptr(), G, self.rank, e, st))
+            check(lib.edgl_xchg_wait(self.base + self.off_fcand, G, e, st))
+            cand = self.base + self.off_cand
+            return topk_merge_raw(cand + K * 4, cand, G, B, K, B * 2 * K, 2 * K, eng.device)
+
+    def close(self):
+        for p in self._opened:
+            self.lib.edgl_xchg_close(p)
+        self._opened = []
+        if self.base:
+            self.lib.edgl_xchg_free(self.base)
+            self.base = 0

@@ -128,6 +128,31 @@ int edgl_logits_topk(edgl_handle* h, const float* y, int64_t y_stride, const int
 int edgl_topk_merge(const float* cand_val, const int32_t* cand_idx, int G, int Bt, int K, int64_t shard_stride,
                     int64_t row_stride, int32_t* idx, float* val, void* stream);
 
+/* ---- fused exchange over peer memory (no reference counterpart: the reference is single-GPU) ----
+ * One process per GPU.  Each rank allocates an exchange region with edgl_xchg_alloc (cudaMalloc + CUDA IPC
+ * handle, zero-filled), ships the 64-byte handle to its peers (any transport) and maps theirs with
+ * edgl_xchg_open.  Kernels then write straight into peer memory over NVLink and raise per-source uint32
+ * flags (system-scope release / acquire); there is no NCCL call on the data path.
+ *   rows region   float  [G*B][d + 2L]  : slot r*B.. holds rank r's packed [y | seqs_i] rows
+ *   cand region   int32  [G][B][2][K]   : block g holds shard g's candidates (idx | val bits) for MY rows
+ *   flags         uint32 [G] per region : flag[g] = last epoch fully written by rank g */
+int edgl_xchg_alloc(int64_t bytes, void** dev_ptr, void* ipc_handle_out /* 64 bytes */);
+int edgl_xchg_open(const void* ipc_handle /* 64 bytes */, void** dev_ptr);
+int edgl_xchg_close(void* dev_ptr);
+int edgl_xchg_free(void* dev_ptr);
+/* Write this rank's B packed rows into slot `rank` of every peer's rows region (peer_rows: device array of G
+ * addresses) and then publish `epoch` in slot `rank` of every peer's flag array (peer_flags: device array). */
+int edgl_xchg_put_rows(edgl_handle* h, const float* y, int64_t y_stride, const int64_t* seqs_i, int B,
+                       const int64_t* peer_rows, const int64_t* peer_flags, int G, int rank, uint32_t epoch,
+                       void* stream);
+/* Enqueue a wait until all G local flags have reached `epoch`. */
+int edgl_xchg_wait(const uint32_t* flags, int G, uint32_t epoch, void* stream);
+/* edgl_logits_topk whose top-K kernel writes the candidates of row R directly into the cand region of rank
+ * R / rows_per_dest (block `rank`) and publishes `epoch` in the peers' cand flags when the step is complete. */
+int edgl_logits_topk_p2p(edgl_handle* h, const float* y, int64_t y_stride, const int64_t* seen_ids, int seen_len,
+                         int64_t seen_stride, int Bt, int rows_per_dest, const int64_t* peer_cand,
+                         const int64_t* peer_flags, int G, int rank, uint32_t epoch, void* stream);
+
 /* ---- layer-level entry points (one per reference layer, for unit parity) ---- */
 /* C.TimeSinusoidCoding(d).code(ts)  (coding.py:132-149): ts fp32 [B,L] already scaled -> [B,L,d]. */
 int edgl_time_sinusoid_code(const float* ts, int B, int L, int d, float* out, void* stream);

@@ -36,6 +36,12 @@ def main():
     ok = torch.equal(got_i, want_i) and torch.equal(got_v, want_v)
     ag_i, ag_v = ShardedRanker(shard, exchange="all_gather").forward_topk(ids, ts, True)
     ok = ok and torch.equal(ag_i, want_i) and torch.equal(ag_v, want_v)
+    pr = ShardedRanker(shard, exchange="p2p")
+    for _ in range(3):  # several epochs through the same peer buffers
+        pi, pv = pr.forward_topk(ids, ts, True)
+        ok = ok and torch.equal(pi, want_i) and torch.equal(pv, want_v)
+    pi2, _ = pr.forward_topk(ids, ts, False)
+    ok = ok and torch.equal(pi2, single.forward_topk(ids, ts, False)[0])
     got_i2, _ = ShardedRanker(shard).forward_topk(ids, ts, False)
     want_i2, _ = single.forward_topk(ids, ts, False)
     ok = ok and torch.equal(got_i2, want_i2)

@@ -244,9 +244,9 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
 // `epoch` into slot `my_rank` of every peer's flag array (the writes of all CTAs are fenced before it).
 __device__ void p2p_signal_when_grid_done(unsigned int* counter, const long long* peer_flags, int G, int my_rank,
                                           uint32_t epoch) {
-  __threadfence_system();
-  __syncthreads();
+  __syncthreads();  // every thread's peer stores are ordered before thread 0 ...
   if (threadIdx.x == 0) {
+    __threadfence_system();  // ... whose system-scope fence is cumulative over them
     const unsigned int prev = atomicAdd(counter, 1u);
     if (prev == gridDim.x - 1) {
       *counter = 0;

@@ -191,9 +191,11 @@ def test_golden_fixtures():
         assert res["bad"] == 0, (f, res)
 
 
-def test_cuda_core_attention_path_agrees():
+@pytest.mark.parametrize("mode", ["simt", "tc"])
+def test_alternative_attention_kernels_agree(mode):
     """EDGL_ATTN=simt forces the CUDA-core attention kernel (the fallback for shapes the tensor-core
-    kernel is not instantiated for); it must satisfy the same parity bar.  Run in a subprocess because
+    kernels are not instantiated for); EDGL_ATTN=tc selects the tcgen05/TMEM kernel (dh=16, E=16, L<=128).
+    Both must satisfy the same parity bar as the default mma.sync kernel.  Run in a subprocess because
     the switch is read once per process."""
     import subprocess
     import sys
@@ -201,7 +203,7 @@ def test_cuda_core_attention_path_agrees():
         "import sys, torch; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
         "from helpers import O, case, assert_close\n"
         "from easydgl_b200.engine import Engine\n"
-        "for name in ('easy_b', 'ctsma_b', 'C1'):\n"
+        "for name in ('easy_b', 'ctsma_b', 'C1', 'C2', 'C3'):\n"
         "    cfg, inp, W = case(name, batch=8)\n"
         "    eng = Engine(cfg, W, max_batch=8, device='cuda:0')\n"
         "    lg = eng.forward_logits(inp['seqs_i'].cuda(), inp['seqs_t'].cuda()).cpu()\n"
@@ -209,6 +211,6 @@ def test_cuda_core_attention_path_agrees():
         "    assert_close(lg[:, 1:], ref[:, 1:], 1e-3, name)\n"
         "print('SIMT_OK')\n" % (os.path.dirname(os.path.abspath(__file__)),
                                 os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
-    env = dict(os.environ, EDGL_ATTN="simt")
+    env = dict(os.environ, EDGL_ATTN=mode)
     res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=280)
     assert "SIMT_OK" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]

@@ -203,13 +203,162 @@ __global__ void __launch_bounds__(128) attention_kernel(AttnArgs a) {
 }
 
 template <int DH, int EMAX>
+static int launch_attention_stream_t(const AttnArgs& a, cudaStream_t st);
+
+template <int DH, int EMAX>
 static int launch_attention_t(const AttnArgs& a, cudaStream_t st) {
   const size_t smem = attn_smem_floats<DH>(a.L, a.E) * sizeof(float);
-  EDGL_REQUIRE(smem <= 227 * 1024, "attention: L=%d dh=%d E=%d needs %zu B of shared memory (> 227 KB)", a.L,
-               DH, a.E, smem);
+  if (smem > 227 * 1024) return launch_attention_stream_t<DH, EMAX>(a, st);  // long sequences: stream the keys
   auto kern = attention_kernel<DH, EMAX>;
   EDGL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<(unsigned)(a.B * a.h), 128, smem, st>>>(a);
+  EDGL_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Key-streaming CUDA-core variant for long sequences (any L; e.g. BASELINE config C5: L=512, dh=32): the
+// same three passes as attention_kernel, but K / T / V / marks are streamed through shared memory in chunks
+// of KT keys, so shared memory no longer grows with L.  Correctness fallback, not a tuned kernel.
+constexpr int KT = 64;
+
+template <int DH, int EMAX>
+__global__ void __launch_bounds__(128) attention_stream_kernel(AttnArgs a, int w1_smem) {
+  extern __shared__ __align__(16) float smem[];
+  const int L = a.L, E = a.E, B = a.B;
+  const int b = blockIdx.x / a.h, hh = blockIdx.x % a.h;
+  const int tid = threadIdx.x;
+  float* Kc = smem;                    // [KT][DH]
+  float* Xc = Kc + KT * DH;            // [KT][DH]  T (pass B) or V (pass C)
+  float* Mc = Xc + KT * DH;            // [KT][E]
+  float* kmc = Mc + KT * E;            // [KT]
+  float* b1 = kmc + KT;                // [DH*E]
+  float* w = b1 + DH * E;              // [E*DH]
+  float* sc = w + E * DH;              // [E]
+  float* W1s = sc + ((E + 3) & ~3);    // [(DH+1)][DH*E] when it fits
+  const float* W1 = w1_smem ? W1s : a.int_w;
+  const long long row0 = (long long)b * L;
+  if (w1_smem)
+    for (int i = tid; i < (DH + 1) * DH * E; i += 128) W1s[i] = a.int_w[i];
+  for (int i = tid; i < DH * E; i += 128) {
+    b1[i] = a.int_b[i];
+    w[i] = a.int_weight[i];
+  }
+  for (int i = tid; i < E; i += 128) sc[i] = expf(a.int_scaling[i]);
+  __syncthreads();
+  constexpr int V4 = DH / 4;
+  auto load_chunk = [&](int k0, const float* X, int ldx, bool with_marks) {
+    __syncthreads();  // previous chunk fully consumed
+    for (int i = tid; i < KT * V4; i += 128) {
+      const int k = i / V4, j = (i % V4) * 4;
+      float4 kk = make_float4(0.f, 0.f, 0.f, 0.f), xx = kk;
+      if (k0 + k < L) {
+        const long long r = row0 + k0 + k;
+        kk = *reinterpret_cast<const float4*>(a.K + r * a.ldk + hh * DH + j);
+        if (X) xx = *reinterpret_cast<const float4*>(X + r * ldx + hh * DH + j);
+      }
+      *reinterpret_cast<float4*>(Kc + k * DH + j) = kk;
+      *reinterpret_cast<float4*>(Xc + k * DH + j) = xx;
+    }
+    if (with_marks)
+      for (int i = tid; i < KT * E; i += 128) {
+        const int k = i / E;
+        Mc[i] = (k0 + k < L) ? (float)a.marks[(row0 + k0 + k) * E + (i % E)] : 0.f;
+      }
+    for (int i = tid; i < KT; i += 128) kmc[i] = (k0 + i < L) ? (a.kmask[row0 + k0 + i] ? 1.f : 0.f) : -1.f;
+    __syncthreads();
+  };
+  const float sqrt_dh = sqrtf((float)DH);
+  for (int q0 = 0; q0 < L; q0 += 128) {
+    const int q = q0 + tid;
+    const bool act = q < L;
+    const long long row = row0 + (act ? q : L - 1);
+    float qv[DH];
+#pragma unroll
+    for (int j = 0; j < DH; j += 4) {
+      const float4 t4 = *reinterpret_cast<const float4*>(a.Q + row * a.ldq + hh * DH + j);
+      qv[j] = t4.x; qv[j + 1] = t4.y; qv[j + 2] = t4.z; qv[j + 3] = t4.w;
+    }
+    auto score = [&](int k0, int k) {
+      float s = __fdiv_rn(dot_dh<DH>(qv, Kc + k * DH), sqrt_dh);
+      if (kmc[k] == 0.f || (a.causal && k0 + k > q)) s = kMaskFill;
+      return s;
+    };
+    float m = -INFINITY;
+    for (int k0 = 0; k0 < L; k0 += KT) {  // pass A: row max
+      load_chunk(k0, nullptr, 0, false);
+      const int kn = min(KT, L - k0);
+      for (int k = 0; k < kn; ++k) m = fmaxf(m, score(k0, k));
+    }
+    float l = 0.f, Hq[DH];
+#pragma unroll
+    for (int j = 0; j < DH; ++j) Hq[j] = 0.f;
+    for (int k0 = 0; k0 < L; k0 += KT) {  // pass B: denominator and H = P T
+      load_chunk(k0, a.T, a.ldt, false);
+      const int kn = min(KT, L - k0);
+      for (int k = 0; k < kn; ++k) {
+        const float p = expf(score(k0, k) - m);
+        l += p;
+#pragma unroll
+        for (int j = 0; j < DH; ++j) Hq[j] = fmaf(p, Xc[k * DH + j], Hq[j]);
+      }
+    }
+    const float inv_l = __frcp_rn(l);
+#pragma unroll
+    for (int j = 0; j < DH; ++j) Hq[j] *= inv_l;
+    float lam[EMAX];
+#pragma unroll
+    for (int e = 0; e < EMAX; ++e) lam[e] = 0.f;
+    intensity_row<DH, EMAX>(Hq, a.spans[row], W1, b1, w, sc, E, lam);
+    if (a.lam && act) {
+      float* lp = a.lam + (((long long)hh * B + b) * L + q) * E;
+#pragma unroll
+      for (int e = 0; e < EMAX; ++e)
+        if (e < E) lp[e] = lam[e];
+    }
+    float Oq[DH];
+#pragma unroll
+    for (int j = 0; j < DH; ++j) Oq[j] = 0.f;
+    for (int k0 = 0; k0 < L; k0 += KT) {  // pass C: O = (G o P) V
+      load_chunk(k0, a.V, a.ldv, true);
+      const int kn = min(KT, L - k0);
+      for (int k = 0; k < kn; ++k) {
+        const float p = expf(score(k0, k) - m) * inv_l;
+        float g = 0.f;
+#pragma unroll
+        for (int e = 0; e < EMAX; ++e)
+          if (e < E) g = fmaf(lam[e], Mc[k * E + e], g);
+        if (a.diag_one && k0 + k == q) g = 1.f;
+        const float gp = g * p;
+#pragma unroll
+        for (int j = 0; j < DH; ++j) Oq[j] = fmaf(gp, Xc[k * DH + j], Oq[j]);
+      }
+    }
+    if (act) {
+      float* op = a.O + row * a.ldo + hh * DH;
+      const float* rp = a.R ? a.R + row * a.ldr + hh * DH : nullptr;
+#pragma unroll
+      for (int j = 0; j < DH; j += 4) {
+        float4 o = make_float4(Oq[j], Oq[j + 1], Oq[j + 2], Oq[j + 3]);
+        if (rp) {
+          const float4 r4 = *reinterpret_cast<const float4*>(rp + j);
+          o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
+        }
+        *reinterpret_cast<float4*>(op + j) = o;
+      }
+    }
+  }
+}
+
+template <int DH, int EMAX>
+static int launch_attention_stream_t(const AttnArgs& a, cudaStream_t st) {
+  const size_t fixed = (size_t)2 * KT * DH + (size_t)KT * a.E + KT + (size_t)2 * DH * a.E + ((a.E + 3) & ~3);
+  const size_t w1 = (size_t)(DH + 1) * DH * a.E;
+  const int w1_smem = (fixed + w1) * sizeof(float) <= 200 * 1024;
+  const size_t smem = (fixed + (w1_smem ? w1 : 0)) * sizeof(float);
+  auto kern = attention_stream_kernel<DH, EMAX>;
+  EDGL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<(unsigned)(a.B * a.h), 128, smem, st>>>(a, w1_smem);
   EDGL_LAUNCH_CHECK();
   return 0;
 }

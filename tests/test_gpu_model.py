@@ -214,3 +214,13 @@ def test_alternative_attention_kernels_agree(mode):
     env = dict(os.environ, EDGL_ATTN=mode)
     res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=280)
     assert "SIMT_OK" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
+
+
+def test_long_sequence_key_streaming_path():
+    """L = 300 (> every register/TMEM-resident kernel's limit) and dh = 32: the key-streaming kernel."""
+    _check_model("easy_b", batch=3, seqslen=299)
+
+
+def test_forward_c5_shape_small():
+    """BASELINE.json configs[4] shape (EasyDGL d=256 L=512 h=8) with a small catalogue and batch."""
+    _check_model("C5", batch=2, num_items=3000)

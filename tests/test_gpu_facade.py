@@ -84,3 +84,26 @@ def test_coding_layer_facades():
     assert_close(tc.code(ts.to(DEV)).cpu(), O.time_sinusoid_code(ts, 16, torch.float64), 1e-5, "tcoding")
     with pytest.raises(AssertionError):
         tc.code(torch.zeros(2, 3, 4, device=DEV))
+
+
+def test_c1_from_tfrecords_end_to_end(tmp_path):
+    """BASELINE.json configs[0] literally: EasyDGL d=64 L=100, 18K-item synthetic Netflix-schema TFRecords,
+    B=32 - file -> reader (dataloader.py conventions) -> model.eval -> HR/NDCG, against the oracle."""
+    from easydgl_b200 import dataloader as D
+    from easydgl_b200.util import ranking
+    cfg = synth.named_config("C1")
+    W = synth.make_weights(cfg, mode="parity")
+    D.write_synthetic_shard(str(tmp_path / "test.tfrec"), cfg, 64, seed=321)
+    flags = _flags(cfg)
+    model = ranking(flags, weights=W, mark_table=W["mark_table"].numpy(), device=DEV)
+    ref_tp = []
+    for features, labels in D.reader(flags, str(tmp_path / "*.tfrec"), is_training=False)(32, device=DEV):
+        assert features["seqs_i"].shape == (32, 100)
+        metrics, idx = model.eval(features, labels, mask_seen=True)
+        ref = O.forward(features["seqs_i"].cpu(), features["seqs_t"].cpu(), W, cfg, dtype=torch.float64)
+        _, ridx = O.eval_topk(ref, features["seqs_i"].cpu(), True, 100, rank_on="probs")
+        assert torch.equal(idx.cpu().long(), ridx), "top-100 must match the oracle on this data"
+        ref_tp.append((ridx, labels[:, -1].cpu()))
+    want = O.ranking_metrics(torch.cat([a for a, _ in ref_tp]), torch.cat([b for _, b in ref_tp]))
+    for k, v in want.items():
+        assert abs(metrics[k] - v) < 1e-9, (k, metrics[k], v)   # streaming means over both batches

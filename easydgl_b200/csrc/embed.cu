@@ -49,8 +49,8 @@ __global__ void __launch_bounds__(128) embed_kernel(EmbedArgs a, float sqrt_d) {
     float2 it = id_ok ? ld2(irow + 2 * j) : make_float2(0.f, 0.f);
     float x0 = __fmul_rn(it.x, sqrt_d), x1 = __fmul_rn(it.y, sqrt_d);  // coding.py:61-63
     if (a.model == 0) {
-      float s, c;
-      sincosf(__fdiv_rn(tsv, a.tscale[j]), &s, &c);  // coding.py:142-145 (divide, accurate sin/cos)
+      float s = 0.f, c = 1.f;  // padded slots have ts = 0 -> code [0, 1, 0, 1, ...] (Q10); warp-uniform branch
+      if (tsv != 0.f) sincosf(__fdiv_rn(tsv, a.tscale[j]), &s, &c);  // coding.py:142-145 (divide, accurate sin/cos)
       x0 = __fadd_rn(x0, s);                         // EasyDGL.py:83
       x1 = __fadd_rn(x1, c);
     }

@@ -169,15 +169,36 @@ struct GroupCtx {
 };
 
 // =================================================================== MMA issuer (one thread per group)
+// A single thread issues ~124 MMAs per item, so the per-MMA instruction overhead IS the tensor-pipe feed rate:
+// every shared-memory descriptor is built once (the operand tiles never move) and advanced by adding the
+// byte offset >> 4 to its start-address field; the loops are unrolled.
 __device__ void run_mma(const AttnArgs& a, const GroupCtx& g, int num_items) {
   const int L = a.L;
   const int NS = (L + 15) & ~15, KSP = (L + 7) >> 3;
   const uint32_t idS = idesc_tf32(NS), id16 = idesc_tf32(16), id64 = idesc_tf32(64);
-  const uint32_t q = smem_u32(g.sm + OFF_Q), k = smem_u32(g.sm + OFF_K), mk = smem_u32(g.sm + OFF_MK),
-                 th = smem_u32(g.sm + OFF_TH), tl = smem_u32(g.sm + OFF_TL), vh = smem_u32(g.sm + OFF_VH),
-                 vl = smem_u32(g.sm + OFF_VL), wh = smem_u32(g.smw), wl = smem_u32(g.smw + W1B);
+  const uint64_t dq = umma_desc(smem_u32(g.sm + OFF_Q)), dk = umma_desc(smem_u32(g.sm + OFF_K)),
+                 dmk = umma_desc(smem_u32(g.sm + OFF_MK)), dth = umma_desc(smem_u32(g.sm + OFF_TH)),
+                 dtl = umma_desc(smem_u32(g.sm + OFF_TL)), dvh = umma_desc(smem_u32(g.sm + OFF_VH)),
+                 dvl = umma_desc(smem_u32(g.sm + OFF_VL)), dwh = umma_desc(smem_u32(g.smw)),
+                 dwl = umma_desc(smem_u32(g.smw + W1B));
   const uint32_t tm = g.tm;
   uint64_t* bar = g.bar;
+  // P V product: A = (hi, lo) copies of a [128 x keys] matrix in TMEM, B = X^T (hi, lo) tiles, 3 products per key step
+  auto pv = [&](uint32_t dacc, uint64_t dxh, uint64_t dxl) {
+#pragma unroll 1
+    for (int ks0 = 0; ks0 < KSP; ks0 += 4) {  // one 32-key atom (2048 B) per outer step
+      const uint64_t ah = dxh + (uint64_t)(ks0 >> 2) * 128, al = dxl + (uint64_t)(ks0 >> 2) * 128;
+      const uint32_t ta = tm + C_S + ks0 * 8, tl_ = tm + C_PL + ks0 * 8;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (ks0 + k < KSP) {
+          mma_ts(dacc, tl_ + k * 8, ah + k * 2, id16, (ks0 + k) != 0);
+          mma_ts(dacc, ta + k * 8, al + k * 2, id16, 1);
+          mma_ts(dacc, ta + k * 8, ah + k * 2, id16, 1);
+        }
+      }
+    }
+  };
   uint32_t n = 0;
   for (int item = g.first_item; item < num_items; item += g.item_stride, ++n) {
     const uint32_t ph = n & 1;
@@ -186,38 +207,33 @@ __device__ void run_mma(const AttnArgs& a, const GroupCtx& g, int num_items) {
     tc_fence_after();
 #pragma unroll
     for (int ks = 0; ks < DH / 8; ++ks) {
-      const uint32_t oh = ks * 32, ol = 64 + ks * 32;
-      mma_ss(tm + C_S, umma_desc(q + ol), umma_desc(k + oh), idS, ks != 0);
-      mma_ss(tm + C_S, umma_desc(q + oh), umma_desc(k + ol), idS, 1);
-      mma_ss(tm + C_S, umma_desc(q + oh), umma_desc(k + oh), idS, 1);
+      const uint64_t oh = ks * 2, ol = 4 + ks * 2;  // byte offsets >> 4
+      mma_ss(tm + C_S, dq + ol, dk + oh, idS, ks != 0);
+      mma_ss(tm + C_S, dq + oh, dk + ol, idS, 1);
+      mma_ss(tm + C_S, dq + oh, dk + oh, idS, 1);
     }
     umma_commit(&bar[B_S]);
     // ---- Hu = P_un T
     mbar_wait(&bar[B_P], ph);
     tc_fence_after();
-    for (int ks = 0; ks < KSP; ++ks) {
-      const uint32_t o = (ks >> 2) * 2048 + (ks & 3) * 32;
-      mma_ts(tm + C_HU, tm + C_PL + ks * 8, umma_desc(th + o), id16, ks != 0);
-      mma_ts(tm + C_HU, tm + C_S + ks * 8, umma_desc(tl + o), id16, 1);
-      mma_ts(tm + C_HU, tm + C_S + ks * 8, umma_desc(th + o), id16, 1);
-    }
+    pv(tm + C_HU, dth, dtl);
     umma_commit(&bar[B_HU]);
     // ---- Z = [H, span, 1] W1'  in four 64-column quarters, two TMEM buffers
     mbar_wait(&bar[B_A], ph);
     tc_fence_after();
-#pragma unroll 1
+#pragma unroll
     for (int qz = 0; qz < 4; ++qz) {
       const int buf = qz & 1;
       const uint32_t use = 2 * n + (qz >> 1);  // how many times this buffer has been handed out before
       mbar_wait(&bar[B_ZF0 + buf], (use & 1) ^ 1);
       tc_fence_after();
-      const uint32_t dz = tm + C_Z + buf * 64, wo = qz * 64 * 128;
+      const uint32_t dz = tm + C_Z + buf * 64;
 #pragma unroll
       for (int ks = 0; ks < 3; ++ks) {
-        const uint32_t o = wo + ks * 32;
-        mma_ts(dz, tm + C_AL + ks * 8, umma_desc(wh + o), id64, ks != 0);
-        mma_ts(dz, tm + C_AH + ks * 8, umma_desc(wl + o), id64, 1);
-        mma_ts(dz, tm + C_AH + ks * 8, umma_desc(wh + o), id64, 1);
+        const uint64_t o = (uint64_t)(qz * 64 * 128 + ks * 32) >> 4;
+        mma_ts(dz, tm + C_AL + ks * 8, dwh + o, id64, ks != 0);
+        mma_ts(dz, tm + C_AH + ks * 8, dwl + o, id64, 1);
+        mma_ts(dz, tm + C_AH + ks * 8, dwh + o, id64, 1);
       }
       umma_commit(&bar[B_Z0 + buf]);
     }
@@ -226,19 +242,14 @@ __device__ void run_mma(const AttnArgs& a, const GroupCtx& g, int num_items) {
     tc_fence_after();
 #pragma unroll
     for (int ks = 0; ks < E / 8; ++ks) {
-      mma_ts(tm + C_G, tm + C_LL + ks * 8, umma_desc(mk + ks * 32), idS, ks != 0);
-      mma_ts(tm + C_G, tm + C_LH + ks * 8, umma_desc(mk + ks * 32), idS, 1);
+      mma_ts(tm + C_G, tm + C_LL + ks * 8, dmk + ks * 2, idS, ks != 0);
+      mma_ts(tm + C_G, tm + C_LH + ks * 8, dmk + ks * 2, idS, 1);
     }
     umma_commit(&bar[B_G]);
     // ---- Ou = (G o P) V
     mbar_wait(&bar[B_GP], ph);
     tc_fence_after();
-    for (int ks = 0; ks < KSP; ++ks) {
-      const uint32_t o = (ks >> 2) * 2048 + (ks & 3) * 32;
-      mma_ts(tm + C_O, tm + C_PL + ks * 8, umma_desc(vh + o), id16, ks != 0);
-      mma_ts(tm + C_O, tm + C_S + ks * 8, umma_desc(vl + o), id16, 1);
-      mma_ts(tm + C_O, tm + C_S + ks * 8, umma_desc(vh + o), id16, 1);
-    }
+    pv(tm + C_O, dvh, dvl);
     umma_commit(&bar[B_O]);
   }
 }

@@ -53,6 +53,7 @@ _SIGS = {
     "edgl_logits_topk_p2p": (_I, [_P, _P, C.c_int64, _P, _I, C.c_int64, _I, _I, _P, _P, _I, _I, C.c_uint32, _P]),
     "edgl_topk_merge": (_I, [_P, _P, _I, _I, _I, C.c_int64, C.c_int64, _P, _P, _P]),
     "edgl_time_sinusoid_code": (_I, [_P, _I, _I, _I, _P, _P]),
+    "edgl_time_function_code": (_I, [_P, _P, _P, C.c_int64, _I, _P, _P]),
     "edgl_embedding_lookup": (_I, [_P, _I, _I, _I, _I, _P, C.c_int64, _P, _P]),
     "edgl_embed": (_I, [_P, _P, _P, _I, _P, _P, _P, _P]),
     "edgl_attention_layer": (_I, [_P, _I, _P, _I, _P, _I, _P, _P, _P, _I, _I, _P, _P, _P]),

@@ -766,6 +766,13 @@ int edgl_time_sinusoid_code(const float* ts, int B, int L, int d, float* out, vo
   return rc;
 }
 
+int edgl_time_function_code(const float* x, const float* basis_freq, const float* phase, int64_t n, int d, float* out,
+                            void* stream) {
+  if (!x || !basis_freq || !phase || !out) return set_error(EDGL_EINVAL, "null argument");
+  EDGL_REQUIRE(n >= 0 && d >= 1, "time_function_code: bad shape");
+  return launch_time_function_code(x, basis_freq, phase, n, d, out, (cudaStream_t)stream);
+}
+
 int edgl_embedding_lookup(const float* table, int vocab, int d, int zero_pad, int scale, const int64_t* ids,
                           int64_t n_ids, float* out, void* stream) {
   if (!table || !ids || !out) return set_error(EDGL_EINVAL, "null argument");
@@ -802,7 +809,9 @@ int edgl_attention_layer(edgl_handle* h, int block, const float* queries, int Cq
     // BiMAU: `keys` and `causality` are ignored by the reference (temporal.py:404-429, Q15)
     EDGL_TRY(dense(queries, Cq, F(w, "qkvt_w"), 4 * d, F(w, "qkvt_b"), h->qkvt, 4 * d, rows, 4 * d, Cq, ACT_NONE,
                    nullptr, 0, st));
-    AttnArgs a = attn_args(h, w, h->qkvt, kmask, intervals, marks, queries, Cq, out, lam, B, false, true);
+    // bit 1 of `causality` selects T.MGAU (temporal.py:455-508): BiMAU without tf.linalg.set_diag
+    AttnArgs a = attn_args(h, w, h->qkvt, kmask, intervals, marks, queries, Cq, out, lam, B, false,
+                           (causality & 2) == 0);
     return launch_attention(a, st);
   }
   if (!keys) return set_error(EDGL_EINVAL, "MAU needs keys");
@@ -810,7 +819,7 @@ int edgl_attention_layer(edgl_handle* h, int block, const float* queries, int Cq
   EDGL_TRY(dense(queries, Cq, F(w, "q_w"), d, F(w, "q_b"), h->qkvt, 4 * d, rows, d, Cq, ACT_NONE, nullptr, 0, st));
   EDGL_TRY(dense(keys, Ck, h->wkvt[block], 3 * d, h->bkvt[block], h->qkvt + d, 4 * d, rows, 3 * d, Ck, ACT_NONE,
                  nullptr, 0, st));
-  AttnArgs a = attn_args(h, w, h->qkvt, kmask, intervals, marks, queries, Cq, out, lam, B, causality != 0, false);
+  AttnArgs a = attn_args(h, w, h->qkvt, kmask, intervals, marks, queries, Cq, out, lam, B, (causality & 1) != 0, false);
   return launch_attention(a, st);
 }
 

@@ -86,6 +86,8 @@ struct EmbedArgs {
 };
 int launch_embed(const EmbedArgs& a, cudaStream_t st);
 int launch_time_code(const float* ts, const float* tscale, long long rows, int d, float* out, cudaStream_t st);
+int launch_time_function_code(const float* x, const float* freq, const float* phase, long long n, int d, float* out,
+                              cudaStream_t st);
 int launch_lookup(const float* table, int vocab, int d, int zero_pad, float scale, const int64_t* ids,
                   long long n, float* out, cudaStream_t st);
 int launch_mark_table_to_u8(const int64_t* src, long long n, uint8_t* dst, int* err_flag, int E, cudaStream_t st);

@@ -117,6 +117,27 @@ int launch_time_code(const float* ts, const float* tscale, long long rows, int d
   return 0;
 }
 
+// C.TimeFunctionCoding.code (coding.py:112-122): the Bochner / Mercer harmonic time kernel of TGAT,
+// out[..., j] = cos(x * basis_freq[j] + phase[j])  (fp32 multiply, then bias_add, then an accurate cos:
+// arguments reach 1e5 rad for day-scaled timestamps, so the fast-math cosine is not an option)
+__global__ void time_function_kernel(const float* __restrict__ x, const float* __restrict__ freq,
+                                     const float* __restrict__ phase, long long n, int d, float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * d) return;
+  const long long r = i / d;
+  const int j = (int)(i % d);
+  out[i] = cosf(__fadd_rn(__fmul_rn(x[r], freq[j]), phase[j]));
+}
+
+int launch_time_function_code(const float* x, const float* freq, const float* phase, long long n, int d, float* out,
+                              cudaStream_t st) {
+  EDGL_REQUIRE(d > 0, "num_units must be positive");
+  if (n == 0) return 0;
+  time_function_kernel<<<cdiv(n * d, 256), 256, 0, st>>>(x, freq, phase, n, d, out);
+  EDGL_LAUNCH_CHECK();
+  return 0;
+}
+
 __global__ void lookup_kernel(const float* __restrict__ table, int vocab, int d, int zero_pad, float scale,
                               const int64_t* __restrict__ ids, long long n, float* __restrict__ out) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;

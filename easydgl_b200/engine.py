@@ -208,7 +208,8 @@ class Engine:
                                       spans.data_ptr(), marks.data_ptr(), _stream()))
         return X0, spans, marks
 
-    def attention_layer(self, block, queries, keys, kmask, intervals, marks, causality=False, want_lam=True):
+    def attention_layer(self, block, queries, keys, kmask, intervals, marks, causality=False, want_lam=True,
+                        no_diag=False):
         queries = _req(queries, torch.float32, "queries", self.device)
         B, L, Cq = queries.shape
         if L != self.L:
@@ -222,7 +223,8 @@ class Engine:
         with torch.cuda.device(self.device):
             check(self.lib.edgl_attention_layer(self._handle, block, queries.data_ptr(), Cq, _ptr(keys_c),
                                                 0 if keys_c is None else keys_c.shape[2], kmask.data_ptr(),
-                                                intervals.data_ptr(), marks.data_ptr(), B, int(bool(causality)),
+                                                intervals.data_ptr(), marks.data_ptr(), B,
+                                                int(bool(causality)) | (2 if no_diag else 0),
                                                 out.data_ptr(), _ptr(lam), _stream()))
         return out, lam
 
@@ -269,6 +271,20 @@ def time_sinusoid_code(ts: torch.Tensor, num_units: int) -> torch.Tensor:
     out = torch.empty((B, L, num_units), dtype=torch.float32, device=ts.device)
     with torch.cuda.device(ts.device):
         check(lib.edgl_time_sinusoid_code(ts.data_ptr(), B, L, num_units, out.data_ptr(), _stream()))
+    return out
+
+
+def time_function_code(x: torch.Tensor, basis_freq: torch.Tensor, phase: torch.Tensor) -> torch.Tensor:
+    """cos(x[..., None] * basis_freq + phase) -> x.shape + (d,)  (C.TimeFunctionCoding, coding.py:112-122)."""
+    lib = _lib.load()
+    x = _req(x, torch.float32, "x")
+    basis_freq = _req(basis_freq, torch.float32, "basis_freq", x.device)
+    phase = _req(phase, torch.float32, "phase", x.device)
+    d = int(basis_freq.numel())
+    out = torch.empty(tuple(x.shape) + (d,), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib.edgl_time_function_code(x.data_ptr(), basis_freq.data_ptr(), phase.data_ptr(), x.numel(), d,
+                                          out.data_ptr(), _stream()))
     return out
 
 

@@ -51,6 +51,22 @@ class PositionCoding(object):
         return self.pembs(pos)
 
 
+class TimeFunctionCoding(object):
+    """coding.py:97-122 (Xu et al., TGAT): learnable harmonic (Bochner / Mercer) time kernel
+    ``cos(t * basis_freq + phase)``; ``basis_freq`` initialised to linspace(0, 9, d), ``phase`` to zeros."""
+
+    def __init__(self, num_units, scope="coding/tif", device="cuda:0", basis_freq=None, phase=None):
+        self._num_units = num_units
+        self.basis_freq = (torch.from_numpy(np.linspace(0, 9, num_units).astype(np.float32)) if basis_freq is None
+                           else basis_freq).to(device=device, dtype=torch.float32)
+        self.phase = (torch.zeros(num_units) if phase is None else phase).to(device=device, dtype=torch.float32)
+
+    def code(self, inputs):
+        batch_size, seqslen = inputs.shape[0], inputs.shape[1]
+        x = inputs.to(torch.float32).reshape(batch_size, seqslen, -1)   # coding.py:114 (tf.to_float + reshape)
+        return _E.time_function_code(x, self.basis_freq, self.phase)     # [B, L, M, d] like tile + cos
+
+
 class TimeSinusoidCoding(object):
     """coding.py:125-149."""
 

@@ -21,6 +21,7 @@ def _glorot(i, o):
 
 class MAU(object):
     _model = "CTSMA"
+    _no_diag = False
 
     def __init__(self, num_units, num_heads, num_events, dropout_rate, scope="modulating_attention", weights=None,
                  device="cuda:0"):
@@ -109,7 +110,7 @@ class MAU(object):
         B, L, cin = queries.shape
         eng = self._engine(B, L, cin)
         return eng.attention_layer(self._block, queries, keys, self._key_mask(masks, B), intervals.to(torch.float32),
-                                   marks.to(torch.uint8), causality=bool(causality))
+                                   marks.to(torch.uint8), causality=bool(causality), no_diag=self._no_diag)
 
 
 class BiMAU(MAU):
@@ -121,3 +122,12 @@ class BiMAU(MAU):
     def __call__(self, queries, keys, masks, intervals, marks, is_training, causality=None):
         # `keys` and `causality` are ignored exactly like the reference (temporal.py:404-429)
         return super().__call__(queries, None, masks, intervals, marks, is_training, False)
+
+
+class MGAU(BiMAU):
+    """temporal.py:455-508: Modulating Gated Attention Unit = BiMAU without ``tf.linalg.set_diag``
+    (instantiated by no model of the reference; provided for completeness)."""
+    _no_diag = True
+
+    def __init__(self, num_units, num_heads, num_events, dropout_rate, scope="GAU_SMA", weights=None, device="cuda:0"):
+        super().__init__(num_units, num_heads, num_events, dropout_rate, scope, weights, device)

@@ -156,6 +156,10 @@ int edgl_logits_topk_p2p(edgl_handle* h, const float* y, int64_t y_stride, const
 /* ---- layer-level entry points (one per reference layer, for unit parity) ---- */
 /* C.TimeSinusoidCoding(d).code(ts)  (coding.py:132-149): ts fp32 [B,L] already scaled -> [B,L,d]. */
 int edgl_time_sinusoid_code(const float* ts, int B, int L, int d, float* out, void* stream);
+/* C.TimeFunctionCoding(d).code(x)  (coding.py:97-122, the Bochner/Mercer harmonic kernel of TGAT; SURVEY 8f
+ * rank 4): x fp32 [n] (any leading shape, flattened) -> out [n,d] = cos(x * basis_freq + phase). */
+int edgl_time_function_code(const float* x, const float* basis_freq, const float* phase, int64_t n, int d, float* out,
+                            void* stream);
 /* C.Embedding(vocab,d,zero_pad,scale)(ids)  (coding.py:45-64): table [vocab,d] raw variable. */
 int edgl_embedding_lookup(const float* table, int vocab, int d, int zero_pad, int scale, const int64_t* ids,
                           int64_t n_ids, float* out, void* stream);
@@ -166,7 +170,9 @@ int edgl_embed(edgl_handle* h, const int64_t* seqs_i, const float* seqs_t, int B
 /* T.BiMAU(...)(queries, keys, masks, intervals, marks, is_training=False)  (temporal.py:404-452)
  * and T.MAU(...)(..., causality)  (temporal.py:335-390), using block `block`'s weights.
  * queries [B,L,Cq]; keys [B,L,Ck] (ignored for EasyDGL handles, Q15); kmask uint8 [B,L] (1 = real key);
- * intervals [B,L]; marks uint8 [B,L,E].  Outputs: out [B,L,d]; lam [h*B,L,E] head-major (may be NULL). */
+ * intervals [B,L]; marks uint8 [B,L,E].  Outputs: out [B,L,d]; lam [h*B,L,E] head-major (may be NULL).
+ * causality: bit 0 = causal mask (MAU only); bit 1 = no set_diag on an EasyDGL handle = T.MGAU
+ * (temporal.py:455-508, identical to BiMAU otherwise). */
 int edgl_attention_layer(edgl_handle* h, int block, const float* queries, int Cq, const float* keys, int Ck,
                          const uint8_t* kmask, const float* intervals, const uint8_t* marks, int B,
                          int causality, float* out, float* lam, void* stream);

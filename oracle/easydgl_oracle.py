@@ -136,6 +136,15 @@ def time_sinusoid_code(ts32: torch.Tensor, num_units: int, dtype) -> torch.Tenso
     return code.reshape(ts32.shape[0], ts32.shape[1], num_units)
 
 
+def time_function_code(inputs: torch.Tensor, basis_freq: torch.Tensor, phase: torch.Tensor, dtype) -> torch.Tensor:
+    """TimeFunctionCoding.code (coding.py:112-122): reshape to [B,L,-1], tile over num_units, x*freq
+    (fp32 multiply) + phase (fp32 bias_add), cos evaluated in ``dtype``."""
+    B, L = inputs.shape[0], inputs.shape[1]
+    x = inputs.to(torch.float32).reshape(B, L, -1).unsqueeze(-1)
+    arg = (x * basis_freq.to(torch.float32) + phase.to(torch.float32)).to(dtype)
+    return torch.cos(arg)
+
+
 # ----------------------------------------------------------------------------
 # src/module/temporal.py
 # ----------------------------------------------------------------------------
@@ -207,6 +216,17 @@ def bimau(queries, kmask, intervals, marks, w, num_units, num_heads, num_events,
     O, lam = _attention_core(Q, K, V, T, kmask, intervals, marks, w, num_heads, num_events,
                              causal=False, diag_one=True, literal=literal)
     O = O + queries[:, :, :d]                                                 # :447
+    return O, lam
+
+
+def mgau(queries, kmask, intervals, marks, w, num_units, num_heads, num_events, literal=False):
+    """MGAU.__call__ (temporal.py:463-508): BiMAU without set_diag."""
+    d = num_units
+    QKVT = queries @ w["qkvt_w"] + w["qkvt_b"]                                # :468
+    Q, K, V, T = torch.split(QKVT, d, dim=-1)
+    O, lam = _attention_core(Q, K, V, T, kmask, intervals, marks, w, num_heads, num_events,
+                             causal=False, diag_one=False, literal=literal)
+    O = O + queries[:, :, :d]                                                 # :503
     return O, lam
 
 

@@ -68,6 +68,23 @@ def test_bimau_layer_facade_signature():
     assert G.shape == (cfg.num_heads * 4, cfg.L, cfg.L)
 
 
+def test_mgau_layer_facade():
+    """T.MGAU (temporal.py:455-508) = BiMAU without set_diag."""
+    from easydgl_b200.module import temporal as T
+    cfg, inp, W = case("easy_c", batch=4, num_events=8)
+    W64 = O._cast(W, torch.float64)
+    X0, kmask, spans, marks = O.easydgl_inputs(inp["seqs_i"], inp["seqs_t"], W64, cfg, torch.float64)
+    blk = W["blocks"][0]
+    keep = {k: blk[k] for k in ("qkvt_w", "qkvt_b", "int_w", "int_b", "int_weight", "int_scaling")}
+    layer = T.MGAU(cfg.num_units, cfg.num_heads, cfg.num_events, 0.1, weights=keep, device=DEV)
+    masks = kmask.float().unsqueeze(1).repeat(cfg.num_heads, cfg.L, 1).to(DEV)
+    out, lam = layer(X0.float().to(DEV), X0.float().to(DEV), masks, spans.float().to(DEV), marks.to(DEV), False)
+    rO, rl = O.mgau(X0, kmask, spans, marks, W64["blocks"][0], cfg.num_units, cfg.num_heads, cfg.num_events)
+    assert_close(out.cpu(), rO, 1e-4, "MGAU out")
+    bO, _ = O.bimau(X0, kmask, spans, marks, W64["blocks"][0], cfg.num_units, cfg.num_heads, cfg.num_events)
+    assert (rO - bO).abs().max() > 1e-6                       # and it differs from BiMAU
+
+
 def test_coding_layer_facades():
     from easydgl_b200.module import coding as C
     g = torch.Generator().manual_seed(3)

@@ -41,6 +41,24 @@ def test_time_sinusoid_code(d):
     assert torch.equal(out[0, 0, 0::2], torch.zeros(d // 2)) and torch.equal(out[0, 0, 1::2], torch.ones(d // 2))
 
 
+def test_time_function_code_bochner_mercer():
+    """C.TimeFunctionCoding.code (coding.py:97-122): cos(t * basis_freq + phase), rank-2 and rank-3 inputs."""
+    from easydgl_b200.module import coding as C
+    g = torch.Generator().manual_seed(8)
+    tc = C.TimeFunctionCoding(24, device=DEV)
+    assert torch.equal(tc.basis_freq.cpu(), torch.linspace(0, 9, 24))
+    ts = (torch.rand(5, 17, generator=g) * 2000 + 10800).float()
+    out = tc.code(ts.to(DEV)).cpu()
+    ref = O.time_function_code(ts, tc.basis_freq.cpu(), tc.phase.cpu(), torch.float64)
+    assert out.shape == (5, 17, 1, 24)
+    assert_close(out, ref, 1e-5, "time function code")
+    iv = (ts[:, :, None] - ts[:, None, :])                       # [B,L,L] interval matrix (TGAT / TGSRec usage)
+    tc2 = C.TimeFunctionCoding(8, device=DEV, phase=torch.randn(8, generator=g))
+    out2 = tc2.code(iv.to(DEV)).cpu()
+    assert out2.shape == (5, 17, 17, 8)
+    assert_close(out2, O.time_function_code(iv, tc2.basis_freq.cpu(), tc2.phase.cpu(), torch.float64), 1e-5, "tif 3-D")
+
+
 def test_time_sinusoid_code_rank_assert():
     from easydgl_b200 import engine
     with pytest.raises(AssertionError):

@@ -7,6 +7,7 @@ stated per assertion; integer outputs bit-exact.
 import math
 
 import pytest
+import numpy as np
 import torch
 
 from helpers import O, assert_close, case, synth
@@ -46,7 +47,7 @@ def test_time_function_code_bochner_mercer():
     from easydgl_b200.module import coding as C
     g = torch.Generator().manual_seed(8)
     tc = C.TimeFunctionCoding(24, device=DEV)
-    assert torch.equal(tc.basis_freq.cpu(), torch.linspace(0, 9, 24))
+    assert np.array_equal(tc.basis_freq.cpu().numpy(), np.linspace(0, 9, 24).astype(np.float32))  # coding.py:109
     ts = (torch.rand(5, 17, generator=g) * 2000 + 10800).float()
     out = tc.code(ts.to(DEV)).cpu()
     ref = O.time_function_code(ts, tc.basis_freq.cpu(), tc.phase.cpu(), torch.float64)

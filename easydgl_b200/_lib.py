@@ -30,6 +30,7 @@ _SIGS = {
     "edgl_last_error": (C.c_char_p, []),
     "edgl_version": (_I, []),
     "edgl_launch_count": (C.c_int64, []),
+    "edgl_crc32c": (C.c_uint32, [C.c_void_p, C.c_size_t, C.c_uint32]),
     "edgl_num_stages": (_I, []),
     "edgl_stage_name": (C.c_char_p, [_I]),
     "edgl_profile": (_I, [_P, _I]),

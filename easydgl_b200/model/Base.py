@@ -4,11 +4,11 @@ of scope and raises."""
 from __future__ import annotations
 
 import abc
-import pickle
 
 import numpy as np
 import torch
 
+from .. import checkpoint
 from .. import engine as _E
 from .. import synth
 
@@ -52,7 +52,7 @@ class Sequential(object):
             return torch.as_tensor(np.asarray(mark_table)).to(torch.int64)
         path = getattr(FLAGS, "mark", None)
         if path:
-            return torch.from_numpy(pickle.load(open(path, 'rb')).toarray()).to(torch.int64)  # EasyDGL.py:45
+            return checkpoint.load_mark_table(path)  # EasyDGL.py:45
         return None
 
     def _setup(self, FLAGS, weights, mark_table, device, max_batch):
@@ -83,6 +83,19 @@ class Sequential(object):
         self.weights = dict(weights)
         if self._engine is not None:
             self._engine.load_weights(self.weights)
+
+    def restore(self, ckpt, overrides=None):
+        """``saver.restore(sess, FLAGS.ckpt)`` (analytics.py:83-88): load the model variables of a
+        ``tf.train.Saver`` checkpoint (prefix, or a directory holding a ``checkpoint`` state file)."""
+        W = checkpoint.load_checkpoint(self.cfg, ckpt, overrides)
+        W["mark_table"] = self.mark_lookup_table
+        self.load_weights(W)
+
+    def save(self, ckpt=None):
+        """``EarlyStopping.save_ckpt`` (util.py:53-55): write the weights as ``ckpt/{model}`` in Saver format."""
+        ckpt = ckpt or "ckpt/%s" % self._model
+        checkpoint.save_checkpoint(self.cfg, self.weights, ckpt)
+        return ckpt
 
     # ---- reference protocol --------------------------------------------------------------------
     @abc.abstractmethod

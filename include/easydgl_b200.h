@@ -23,6 +23,7 @@
 #ifndef EASYDGL_B200_H
 #define EASYDGL_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -64,6 +65,10 @@ const char* edgl_last_error(void);
 int edgl_version(void);
 /* Number of CUDA kernels this library has launched in this process (bench.py's gpu_launches). */
 int64_t edgl_launch_count(void);
+/* Host-side CRC32C (Castagnoli) of data[0..n), continuing from `crc` (0 to start).  Replaces the checksum
+ * TensorFlow applies to TFRecord frames (tf.data.TFRecordDataset, dataloader.py:230-236) and to the
+ * tensor bundles of tf.train.Saver (util.py:26,53-55); no device work, callable without a GPU. */
+uint32_t edgl_crc32c(const void* data, size_t n, uint32_t crc);
 
 /* Optional per-stage device timing (no reference counterpart; the reference has no profiler).
  * While enabled, a CUDA event is recorded on the caller's stream before every kernel of the pipeline;

@@ -128,3 +128,28 @@ def test_c1_from_tfrecords_end_to_end(tmp_path):
     want = O.ranking_metrics(torch.cat([a for a, _ in ref_tp]), torch.cat([b for _, b in ref_tp]))
     for k, v in want.items():
         assert abs(metrics[k] - v) < 1e-9, (k, metrics[k], v)
+
+
+@pytest.mark.parametrize("name", ["easy_b", "ctsma_a"])
+def test_restore_from_saver_checkpoint_and_mark_pkl(tmp_path, name):
+    """analytics.py:83-90 flow: FLAGS.mark -> mark.pkl, model built with fresh variables, then
+    saver.restore(sess, FLAGS.ckpt); logits must equal those of a model given the weights directly."""
+    from easydgl_b200 import checkpoint as CK
+    from easydgl_b200.util import ranking
+    cfg, inp, W = case(name, batch=6)
+    CK.save_mark_table(str(tmp_path / "mark.pkl"), W["mark_table"])
+    trained = ranking(_flags(cfg), weights=W, mark_table=W["mark_table"].numpy(), device=DEV)
+    prefix = trained.save(str(tmp_path / "ckpt" / cfg.model))                 # util.py:53-55
+    features = {"seqs_i": inp["seqs_i"].to(DEV), "seqs_t": inp["seqs_t"].to(DEV)}
+    want = trained(features, False).cpu()
+    flags = _flags(cfg)
+    flags.mark = str(tmp_path / "mark.pkl")
+    fresh = ranking(flags, device=DEV)                                       # tf default initialisers
+    assert torch.equal(fresh.mark_lookup_table, W["mark_table"])
+    before = fresh(features, False).cpu()
+    assert not torch.equal(before, want)
+    fresh.restore(prefix)                                                    # engine already built: weights rebind
+    assert torch.equal(fresh(features, False).cpu(), want)
+    again = ranking(flags, device=DEV)
+    again.restore(str(tmp_path / "ckpt"))                                    # directory with a `checkpoint` file
+    assert torch.equal(again(features, False).cpu(), want)

@@ -67,6 +67,7 @@ struct edgl_handle {
   float* wfold0 = nullptr;     // EasyDGL block 0: [Ka,4d]
   float* pbias0 = nullptr;     // EasyDGL block 0: [L,4d] = pos_embs @ W[d:2d] + b
   std::vector<float*> wkvt, bkvt;  // CTSMA: packed [Cin,3d], [3d]
+  std::vector<unsigned char*> mlp_pack;  // per block: intensity-MLP constants for attn_f16.cu (null if not covered)
   // K-major ([N,K]) copies of every dense kernel for the tensor-core GEMM (made in edgl_commit)
   float* wfold0T = nullptr;                               // [4d, Ka]
   std::vector<std::map<std::string, float*>> btT;         // per block: name -> [N,K]
@@ -210,6 +211,9 @@ AttnArgs attn_args(const edgl_handle* h, const std::map<std::string, Tensor>& w,
   a.int_scaling = F(w, "int_scaling");
   a.O = O; a.ldo = d; a.lam = lam; a.B = B; a.L = h->L; a.d = d; a.h = h->h; a.E = h->E;
   a.causal = causal; a.diag_one = diag_one;
+  a.mlp_pack = nullptr;
+  for (size_t i = 0; i < h->bt.size() && i < h->mlp_pack.size(); ++i)
+    if (&h->bt[i] == &w) a.mlp_pack = h->mlp_pack[i];
   return a;
 }
 
@@ -579,6 +583,16 @@ int edgl_commit(edgl_handle* h, void* stream) {
         EDGL_CUDA(cudaMemcpyAsync(h->bkvt[i] + j * d, F(w, bn[j]), (size_t)d * sizeof(float),
                                   cudaMemcpyDeviceToDevice, st));
       }
+    }
+  }
+  // intensity-MLP constants in the fragment layout of the 3xFP16 attention kernel (attn_f16.cu)
+  if (const size_t pb = attention_f16_pack_bytes(h->dh, E)) {
+    h->mlp_pack.resize(h->cfg.num_blocks, nullptr);
+    for (int i = 0; i < h->cfg.num_blocks; ++i) {
+      const auto& w = h->bt[i];
+      if (!h->mlp_pack[i]) EDGL_TRY(dev_alloc(h, &h->mlp_pack[i], pb));
+      EDGL_TRY(launch_attention_f16_pack(F(w, "int_w"), F(w, "int_b"), F(w, "int_weight"), F(w, "int_scaling"), h->dh,
+                                         E, h->mlp_pack[i], st));
     }
   }
   // K-major copies of the dense kernels for the tcgen05 GEMM (allocated once, refreshed on every commit)

@@ -387,6 +387,11 @@ int launch_attention(const AttnArgs& a, cudaStream_t st) {
     const int r = launch_attention_tc(a, st);
     if (r <= 0) return r;
   }
+  // EDGL_ATTN=f16: the scaled 3xFP16 mma.sync kernel (attn_f16.cu; dh = 16, E = 16, L <= 208)
+  if (mode == 'f') {
+    const int r = launch_attention_f16(a, st);
+    if (r <= 0) return r;
+  }
   if (!force_simt) {  // EDGL_ATTN=mma: the mma.sync kernel; EDGL_ATTN=simt: the CUDA-core kernel
     int r = 1;
     if (dh == 8) r = launch_attention_mma_dh8(a, st);

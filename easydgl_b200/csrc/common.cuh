@@ -55,6 +55,7 @@ enum Act { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2 };
 struct GemmArgs {
   const float* A = nullptr; int lda = 0;
   const float* W = nullptr; int ldw = 0; bool w_is_nk = false;
+  const float* Wlo = nullptr;  // optional, w_is_nk only: W - tf32(W) in the layout of W (constant weights, made at commit)
   float* C = nullptr; int ldc = 0;
   int M = 0, N = 0, K = 0;
   const float* bias = nullptr;                 // [N] or null
@@ -67,6 +68,7 @@ int launch_gemm(const GemmArgs& a, cudaStream_t st);
 bool gemm_tc_supported(const GemmArgs& a);
 int launch_gemm_tc(const GemmArgs& a, cudaStream_t st);
 int launch_transpose(const float* in, int rows, int cols, float* out, cudaStream_t st);
+int launch_tf32_lo(const float* in, long long n, float* out, cudaStream_t st);  // out = in - (in with 13 low mantissa bits cleared)
 
 struct EmbedArgs {
   int model;  // 0 EasyDGL, 1 CTSMA
@@ -106,8 +108,14 @@ struct AttnArgs {
   float* lam;                // [h*B, L, E] or null
   int B, L, d, h, E;
   bool causal, diag_one;
+  const void* mlp_pack = nullptr;  // attn_f16.cu: constants of the intensity MLP packed at commit, or null
 };
 int launch_attention(const AttnArgs& a, cudaStream_t st);
+// scaled 3xFP16 mma.sync kernel (attn_f16.cu): 0 = launched, 1 = shape not covered, <0 = error
+int launch_attention_f16(const AttnArgs& a, cudaStream_t st);
+size_t attention_f16_pack_bytes(int dh, int E);  // 0 if the shape is not covered
+int launch_attention_f16_pack(const float* int_w, const float* int_b, const float* int_weight, const float* int_scaling,
+                              int dh, int E, void* pack, cudaStream_t st);
 int launch_attention_tc(const AttnArgs& a, cudaStream_t st);
 int launch_intensity(const float* H, const float* spans, const uint8_t* marks, const float* int_w,
                      const float* int_b, const float* int_weight, const float* int_scaling, int B, int L,

@@ -206,6 +206,22 @@ int launch_transpose(const float* in, int rows, int cols, float* out, cudaStream
   return 0;
 }
 
+__global__ void tf32_lo_kernel(const float* __restrict__ in, long long n, float* __restrict__ out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float x = in[i];
+    out[i] = x - __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+  }
+}
+
+int launch_tf32_lo(const float* in, long long n, float* out, cudaStream_t st) {
+  if (n == 0) return 0;
+  long long blocks = (n + 255) / 256;
+  if (blocks > 4096) blocks = 4096;
+  tf32_lo_kernel<<<(unsigned)blocks, 256, 0, st>>>(in, n, out);
+  EDGL_LAUNCH_CHECK();
+  return 0;
+}
+
 int launch_gemm(const GemmArgs& a, cudaStream_t st) {
   EDGL_REQUIRE(a.M >= 0 && a.N > 0 && a.K > 0, "gemm: bad shape M=%d N=%d K=%d", a.M, a.N, a.K);
   if (a.M == 0) return 0;

@@ -132,6 +132,8 @@ struct Params {
   int act;
   int col0_bias_only;  // tied zero-padded table: column 0 is exactly the bias (coding.py:56-57)
   int ntn, num_tiles, kblocks;
+  int has_blo;  // W_lo = W - tf32(W) is pre-computed in global memory (weights are constant after commit): TMA brings
+                // it in like W and the splitter warps only split the activations
   long long* dbg;  // optional [gridDim][8] cycle counters (EDGL_TC_DEBUG), else null
 };
 
@@ -150,7 +152,8 @@ struct Smem {
 
 template <int BN, int ACT>
 __global__ void __launch_bounds__(NTHREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, Params p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+               const __grid_constant__ CUtensorMap mapBlo, Params p) {
   using SM = Smem<BN>;
   constexpr int S = SM::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -199,6 +202,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapA)) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapB)) : "memory");
+      if (p.has_blo) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapBlo)) : "memory");
       uint32_t it = 0;
       // the activations stream from HBM exactly once: pull the A rows of the NEXT tile into L2 while the
       // current tile is computed, so the TMA loads below see L2 latency instead of DRAM latency
@@ -212,9 +216,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           const long long t0 = clock64();
           mbar_wait(&empty[s], ((it / S) & 1) ^ 1);
           dbg_acc[0] += clock64() - t0;
-          mbar_expect_tx(&full[s], SM::A_BYTES + SM::B_BYTES);
+          mbar_expect_tx(&full[s], SM::A_BYTES + (p.has_blo ? 2 * SM::B_BYTES : SM::B_BYTES));
           tma_load_2d(&mapA, &full[s], stA(s), kb * BK, m0);
           tma_load_2d(&mapB, &full[s], stB(s), kb * BK, n0);
+          if (p.has_blo) tma_load_2d(&mapBlo, &full[s], stBlo(s), kb * BK, n0);
         }
       }
     }
@@ -277,8 +282,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         };
 #pragma unroll 4
         for (int i = t; i < SM::A_BYTES / 16; i += 128) al[i] = lo4(a[i]);
+        if (!p.has_blo) {
 #pragma unroll 4
-        for (int i = t; i < SM::B_BYTES / 16; i += 128) bl[i] = lo4(b[i]);
+          for (int i = t; i < SM::B_BYTES / 16; i += 128) bl[i] = lo4(b[i]);
+        }
         fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
         mbar_arrive(&split[s]);
         dbg_acc[4] += clock64() - t1;
@@ -459,13 +466,17 @@ int launch_gemm_tc(const GemmArgs& a, cudaStream_t st) {
   }();
   if (a.M == 0) return 0;
   const int bn = a.N > 128 ? 256 : 128;
-  CUtensorMap mapA, mapB;
+  CUtensorMap mapA, mapB, mapBlo;
   EDGL_TRY(make_map(&mapA, a.A, a.M, a.K, a.lda, BM));
   EDGL_TRY(make_map(&mapB, a.W, a.N, a.K, a.ldw, bn));
+  static const bool no_blo = getenv("EDGL_TC_NOBLO") != nullptr;  // A/B switch for measurements
+  const bool has_blo = a.Wlo != nullptr && !no_blo && (reinterpret_cast<uintptr_t>(a.Wlo) & 15) == 0;
+  EDGL_TRY(make_map(&mapBlo, has_blo ? a.Wlo : a.W, a.N, a.K, a.ldw, bn));
   Params p;
   p.C = a.C; p.ldc = a.ldc; p.M = a.M; p.N = a.N; p.K = a.K; p.bias = a.bias; p.pbias = a.pbias;
   p.pperiod = a.pperiod > 0 ? a.pperiod : 1; p.R = a.R; p.ldr = a.ldr; p.act = a.act;
   p.col0_bias_only = a.zero_wrow0 ? 1 : 0;
+  p.has_blo = has_blo ? 1 : 0;
   p.ntn = cdiv(a.N, bn);
   const long long ntm = cdiv(a.M, BM);
   EDGL_REQUIRE(ntm * p.ntn < (1ll << 31), "gemm_tc: too many tiles");
@@ -484,7 +495,7 @@ int launch_gemm_tc(const GemmArgs& a, cudaStream_t st) {
   {                                                                                                            \
     auto kern = gemm_tc_kernel<BNV, ACTV>;                                                                     \
     EDGL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BNV>::BYTES));      \
-    kern<<<grid, NTHREADS, Smem<BNV>::BYTES, st>>>(mapA, mapB, p);                                             \
+    kern<<<grid, NTHREADS, Smem<BNV>::BYTES, st>>>(mapA, mapB, mapBlo, p);                                            \
   }
   if (bn == 256) {
     if (a.act == ACT_GELU) EDGL_TC_LAUNCH(256, ACT_GELU)

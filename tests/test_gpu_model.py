@@ -191,7 +191,7 @@ def test_golden_fixtures():
         assert res["bad"] == 0, (f, res)
 
 
-@pytest.mark.parametrize("mode", ["simt", "tc"])
+@pytest.mark.parametrize("mode", ["simt", "tc", "mma", "f16"])
 def test_alternative_attention_kernels_agree(mode):
     """EDGL_ATTN=simt forces the CUDA-core attention kernel (the fallback for shapes the tensor-core
     kernels are not instantiated for); EDGL_ATTN=tc selects the tcgen05/TMEM kernel (dh=16, E=16, L<=128).
@@ -214,6 +214,19 @@ def test_alternative_attention_kernels_agree(mode):
     env = dict(os.environ, EDGL_ATTN=mode)
     res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=280)
     assert "SIMT_OK" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
+
+
+@pytest.mark.parametrize("mode", ["mma", "f16"])
+def test_attention_variant_layers(mode):
+    """Layer-level (BiMAU / MAU) and model-level parity of one tensor-core attention kernel at fp32-level
+    tolerance (2e-5 of max|ref| vs the fp64 oracle), with Q/K/V/T/MLP operands rescaled by up to 2^+-40: the
+    scaled 3xFP16 kernel (attn_f16.cu) must hold the same accuracy as the 3xTF32 one over the whole range."""
+    import subprocess
+    import sys
+    script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "attn_variant_check.py")
+    env = dict(os.environ, EDGL_ATTN=mode)
+    res = subprocess.run([sys.executable, script], env=env, capture_output=True, text=True, timeout=280)
+    assert "VARIANT_OK" in res.stdout, res.stdout[-3000:] + res.stderr[-2000:]
 
 
 def test_long_sequence_key_streaming_path():

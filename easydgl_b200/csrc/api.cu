@@ -64,6 +64,7 @@ struct edgl_handle {
   int* flag = nullptr;
   unsigned int* p2p_counter = nullptr;  // grid-done counters of the fused-exchange kernels (zero-initialised)
   float* bias_full = nullptr;  // [N1] = concat([-1000], output_bias)  (Base.py:110)
+  float* table_lo = nullptr;   // [c1-c0, d] tf32 lo part of the owned item-table rows (logits GEMM), or null
   float* wfold0 = nullptr;     // EasyDGL block 0: [Ka,4d]
   float* pbias0 = nullptr;     // EasyDGL block 0: [L,4d] = pos_embs @ W[d:2d] + b
   std::vector<float*> wkvt, bkvt;  // CTSMA: packed [Cin,3d], [3d]
@@ -192,9 +193,10 @@ int dense(const float* A, int lda, const float* W, int ldw, const float* bias, f
 
 // dense layer with a K-major ([N,K]) kernel -> tensor-core path
 int dense_nk(const float* A, int lda, const float* Wt, int K, const float* bias, float* C, int ldc, long long M, int N,
-             int act, const float* R, int ldr, cudaStream_t st) {
+             int act, const float* R, int ldr, cudaStream_t st, bool has_lo = true) {
   GemmArgs g;
   g.A = A; g.lda = lda; g.W = Wt; g.ldw = K; g.w_is_nk = true; g.C = C; g.ldc = ldc;
+  if (has_lo) g.Wlo = Wt + (size_t)N * K;  // every K-major copy made by edgl_commit is followed by its tf32 lo part
   g.M = (int)M; g.N = N; g.K = K; g.bias = bias; g.act = act; g.R = R; g.ldr = ldr;
   return launch_gemm(g, st);
 }
@@ -245,6 +247,7 @@ int encode_easydgl(edgl_handle* h, const int64_t* ids, const float* ts, int B, f
       // QKVT = X0 @ W + b with the position / mark-code thirds of X0 folded (commit()): temporal.py:409
       GemmArgs g;
       g.A = h->xa; g.lda = h->Ka; g.W = h->wfold0T; g.ldw = h->Ka; g.w_is_nk = true; g.C = h->qkvt; g.ldc = 4 * d;
+      g.Wlo = h->wfold0T + (size_t)h->Ka * 4 * d;
       g.M = (int)rows; g.N = 4 * d; g.K = h->Ka; g.pbias = h->pbias0; g.pperiod = L;
       EDGL_TRY(launch_gemm(g, st));
     } else {
@@ -324,6 +327,7 @@ int logits_rows(edgl_handle* h, const float* y, int ldy, long long rc, float* ou
   GemmArgs g;
   g.A = y; g.lda = ldy;
   g.W = F(h->mt, "item_embs") + h->c0 * h->d; g.ldw = h->d; g.w_is_nk = true;
+  g.Wlo = h->table_lo;
   g.zero_wrow0 = (h->c0 == 0);  // zero_pad=True: row 0 of the tied table is zeros (coding.py:56-57)
   g.C = out; g.ldc = ldo; g.M = (int)rc; g.N = (int)(h->c1 - h->c0); g.K = h->d;
   g.bias = h->bias_full + h->c0;
@@ -595,13 +599,22 @@ int edgl_commit(edgl_handle* h, void* stream) {
                                          E, h->mlp_pack[i], st));
     }
   }
+  // tf32 lo part of the owned rows of the tied item table (B operand of the logits GEMM); skipped above 2 GiB
+  {
+    const long long n = (h->c1 - h->c0) * (long long)d;
+    if (n * 4 <= (2ll << 30)) {
+      if (!h->table_lo) EDGL_TRY(dev_alloc(h, &h->table_lo, (size_t)n));
+      EDGL_TRY(launch_tf32_lo(F(h->mt, "item_embs") + h->c0 * d, n, h->table_lo, st));
+    }
+  }
   // K-major copies of the dense kernels for the tcgen05 GEMM (allocated once, refreshed on every commit)
   {
     auto transposed = [&](std::map<std::string, float*>& dst, const std::string& key, const float* src, int K,
                           int N) -> int {
       float*& buf = dst[key];
-      if (!buf) EDGL_TRY(dev_alloc(h, &buf, (size_t)K * N));
-      return launch_transpose(src, K, N, buf, st);
+      if (!buf) EDGL_TRY(dev_alloc(h, &buf, (size_t)2 * K * N));  // [N,K] copy, then its tf32 lo part (gemm_tc.cu)
+      EDGL_TRY(launch_transpose(src, K, N, buf, st));
+      return launch_tf32_lo(buf, (long long)K * N, buf + (size_t)K * N, st);
     };
     for (int i = 0; i < h->cfg.num_blocks; ++i) {
       const auto& w = h->bt[i];
@@ -620,8 +633,9 @@ int edgl_commit(edgl_handle* h, void* stream) {
     }
     if (easy) {
       EDGL_TRY(transposed(h->mtT, "tr_w", F(h->mt, "tr_w"), d, d));
-      if (!h->wfold0T) EDGL_TRY(dev_alloc(h, &h->wfold0T, (size_t)h->Ka * 4 * d));
+      if (!h->wfold0T) EDGL_TRY(dev_alloc(h, &h->wfold0T, (size_t)2 * h->Ka * 4 * d));
       EDGL_TRY(launch_transpose(h->wfold0, h->Ka, 4 * d, h->wfold0T, st));
+      EDGL_TRY(launch_tf32_lo(h->wfold0T, (long long)h->Ka * 4 * d, h->wfold0T + (size_t)h->Ka * 4 * d, st));
     }
   }
   int flag = 0;
@@ -865,7 +879,7 @@ int edgl_dense_nk(const float* x, const float* wt, const float* b, int M, int K,
                   void* stream) {
   if (!x || !wt || !out) return set_error(EDGL_EINVAL, "null argument");
   EDGL_REQUIRE(act >= 0 && act <= 2, "dense: unknown activation %d", act);
-  return dense_nk(x, K, wt, K, b, out, N, M, N, act, nullptr, 0, (cudaStream_t)stream);
+  return dense_nk(x, K, wt, K, b, out, N, M, N, act, nullptr, 0, (cudaStream_t)stream, false);
 }
 
 int edgl_topk(float* logits, int B, int N, const int64_t* seen_ids, int seen_len, int K, int32_t* idx, float* val,

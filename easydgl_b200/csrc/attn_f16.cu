@@ -63,10 +63,12 @@ struct F16Layout {
   static constexpr int SC_OFF = WV_OFF + NC * 4;            // exp(scaling) [E]
   static constexpr int MISC_OFF = SC_OFF + E * 4;           // {1 / scale(W1), 0, 0, 0}
   static constexpr int PACK_BYTES = MISC_OFF + 16;
-  __host__ __device__ static constexpr int svw(int NB) { return NB * 16 + ((NB % 2 == 0) ? 16 : 0); }
+  // K / V / T rows in shared memory: [key]{hi[DH] | lo[DH] | 16 B pad} fp16; an odd number of 16-byte chunks per
+  // row keeps the eight row addresses of an ldmatrix phase on distinct bank groups
+  static constexpr int RB = 4 * DH + 16;
   __host__ __device__ static constexpr size_t smem_bytes(int NT) {
-    const int NB = (NT + 1) / 2, LP = NT * 8;
-    return (size_t)PACK_BYTES + (size_t)LP * SKW * 4 + 2 * (size_t)DH * svw(NB) * 4 + (size_t)LP * 32 + (size_t)LP * 4 + 32;
+    const int NB = (NT + 1) / 2, LP = NT * 8, RP = NB * 16;
+    return (size_t)PACK_BYTES + 3 * (size_t)RP * RB + (size_t)LP * 32 + (size_t)LP * 4 + 32;
   }
 };
 
@@ -111,13 +113,27 @@ __global__ void __launch_bounds__(256) mlp_pack_kernel(const float* __restrict__
   if (threadIdx.x < 4) misc[threadIdx.x] = threadIdx.x == 0 ? isw : 0.f;
 }
 
-// out[ND][4] = A[NT][.] (accumulator layout: rows g / g+8, keys nt*8 + 2t + (c&1)) times X, with X^T staged as
-// [dim][16-key block][lane t]{hi(2t,2t+1), hi(2t+8,2t+9), lo, lo}.  Two key blocks are in flight on separate
-// accumulators so an accumulator is touched once per 2*ND MMAs.
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t saddr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], uint32_t saddr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr));
+}
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// out[ND][4] = A[NT][.] (accumulator layout: rows g / g+8, keys nt*8 + 2t + (c&1)) times X, X staged row-major as
+// [key]{hi[DH] | lo[DH] | pad} fp16 and read with ldmatrix.trans (xs = this lane's row address for key block 0,
+// dims 0..15, hi).  Two key blocks are in flight on separate accumulators, so an accumulator is touched once per
+// 2*ND MMAs.
 template <int DH, int NT>
-__device__ __forceinline__ void pv_product16(const float (&P)[NT][4], const uint32_t* Xt, int SVW, float (&out)[DH / 8][4],
-                                             int g, int t) {
-  constexpr int ND = DH / 8, NB = (NT + 1) / 2;
+__device__ __forceinline__ void pv_product16(const float (&P)[NT][4], uint32_t xs, float (&out)[DH / 8][4]) {
+  constexpr int ND = DH / 8, NB = (NT + 1) / 2, RB = F16Layout<DH>::RB;
   float acc[2][ND][4];
 #pragma unroll
   for (int p = 0; p < 2; ++p)
@@ -126,7 +142,7 @@ __device__ __forceinline__ void pv_product16(const float (&P)[NT][4], const uint
 #pragma unroll
   for (int j0 = 0; j0 < NB; j0 += 2) {
     uint32_t ah[2][4], al[2][4];
-    uint4 xb[2][ND];
+    uint32_t xh[2][ND / 2][4], xl[2][ND / 2][4];
 #pragma unroll
     for (int p = 0; p < 2; ++p)
       if (j0 + p < NB) {
@@ -140,24 +156,26 @@ __device__ __forceinline__ void pv_product16(const float (&P)[NT][4], const uint
           ah[p][2] = ah[p][3] = al[p][2] = al[p][3] = 0u;
         }
 #pragma unroll
-        for (int n = 0; n < ND; ++n)
-          xb[p][n] = *reinterpret_cast<const uint4*>(Xt + (size_t)(n * 8 + g) * SVW + j * 16 + t * 4);
+        for (int np = 0; np < ND / 2; ++np) {
+          ldsm_x4_trans(xh[p][np], xs + j * 16 * RB + np * 32);
+          ldsm_x4_trans(xl[p][np], xs + j * 16 * RB + np * 32 + DH * 2);
+        }
       }
 #pragma unroll
     for (int p = 0; p < 2; ++p)
       if (j0 + p < NB)
 #pragma unroll
-        for (int n = 0; n < ND; ++n) mma_f16(acc[p][n], al[p], xb[p][n].x, xb[p][n].y);
+        for (int n = 0; n < ND; ++n) mma_f16(acc[p][n], al[p], xh[p][n >> 1][(n & 1) * 2], xh[p][n >> 1][(n & 1) * 2 + 1]);
 #pragma unroll
     for (int p = 0; p < 2; ++p)
       if (j0 + p < NB)
 #pragma unroll
-        for (int n = 0; n < ND; ++n) mma_f16(acc[p][n], ah[p], xb[p][n].z, xb[p][n].w);
+        for (int n = 0; n < ND; ++n) mma_f16(acc[p][n], ah[p], xl[p][n >> 1][(n & 1) * 2], xl[p][n >> 1][(n & 1) * 2 + 1]);
 #pragma unroll
     for (int p = 0; p < 2; ++p)
       if (j0 + p < NB)
 #pragma unroll
-        for (int n = 0; n < ND; ++n) mma_f16(acc[p][n], ah[p], xb[p][n].x, xb[p][n].y);
+        for (int n = 0; n < ND; ++n) mma_f16(acc[p][n], ah[p], xh[p][n >> 1][(n & 1) * 2], xh[p][n >> 1][(n & 1) * 2 + 1]);
   }
 #pragma unroll
   for (int n = 0; n < ND; ++n)
@@ -165,22 +183,37 @@ __device__ __forceinline__ void pv_product16(const float (&P)[NT][4], const uint
     for (int c = 0; c < 4; ++c) out[n][c] = acc[0][n][c] + acc[1][n][c];
 }
 
-// NT = number of 8-key tiles held in registers (L <= 8*NT); HPC heads are processed by one CTA in turn
-template <int DH, int NT, int MINB>
-__global__ void __launch_bounds__(((NT + 1) / 2 > 8 ? 8 : (NT + 1) / 2) * 32, MINB) attention_f16_kernel(AttnArgs a, int hpc) {
+__device__ __forceinline__ float absmax4(float m, const float4& v) {
+  return fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+}
+// 4 consecutive dims of one key -> 8 bytes of hi and 8 bytes of lo in the key's row
+__device__ __forceinline__ void put4(unsigned char* row, int dim0, int DH2, const float4& v, float s) {
+  uint2 hi, lo;
+  split2(v.x * s, v.y * s, hi.x, lo.x);
+  split2(v.z * s, v.w * s, hi.y, lo.y);
+  *reinterpret_cast<uint2*>(row + dim0 * 2) = hi;
+  *reinterpret_cast<uint2*>(row + DH2 + dim0 * 2) = lo;
+}
+
+// NT = number of 8-key tiles held in registers (L <= 8*NT); HPC heads are processed by one CTA in turn.
+// MAXREG bounds the registers per thread and so the CTAs per SM (7 warps/CTA at L = 100: 128 -> 2, 80 -> 3, 72 -> 4).
+template <int DH, int NT, int MAXREG>
+__global__ void __maxnreg__(MAXREG) attention_f16_kernel(AttnArgs a, int hpc) {
   using LY = F16Layout<DH>;
-  constexpr int E = LY::E, KD = LY::KD, ND = LY::ND, NC = LY::NC, MT = LY::MT, SKW = LY::SKW;
-  constexpr int NB = (NT + 1) / 2, LP = NT * 8, SVW = LY::svw(NB);
+  constexpr int E = LY::E, KD = LY::KD, ND = LY::ND, NC = LY::NC, MT = LY::MT, SKW = LY::SKW, RB = LY::RB;
+  constexpr int NB = (NT + 1) / 2, LP = NT * 8, RP = NB * 16;
+  constexpr int V4 = DH / 4;
+  constexpr int KI = (NT * 8 * V4 + 255) / 256 < 2 ? 2 : (NT * 8 * V4 + 255) / 256;  // (key, 4 dims) items per thread
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const uint32_t* W1t = reinterpret_cast<const uint32_t*>(smem_raw);                  // [NC][SKW]
   const float4* bw = reinterpret_cast<const float4*>(smem_raw + LY::BW_OFF);          // [NC/2]
   const float* wv = reinterpret_cast<const float*>(smem_raw + LY::WV_OFF);            // [NC]
   const float* sc = reinterpret_cast<const float*>(smem_raw + LY::SC_OFF);            // [E]
   const float* misc = reinterpret_cast<const float*>(smem_raw + LY::MISC_OFF);
-  uint32_t* Ks = reinterpret_cast<uint32_t*>(smem_raw + LY::PACK_BYTES);              // [LP][SKW]
-  uint32_t* Vt = Ks + LP * SKW;                                                       // [DH][SVW]
-  uint32_t* Tt = Vt + DH * SVW;                                                       // [DH][SVW]
-  uint32_t* Ms = Tt + DH * SVW;                                                       // [LP][8] marks as fp16
+  unsigned char* Ks = smem_raw + LY::PACK_BYTES;                                      // [RP] rows of RB bytes
+  unsigned char* Vs = Ks + RP * RB;
+  unsigned char* Ts = Vs + RP * RB;
+  uint32_t* Ms = reinterpret_cast<uint32_t*>(Ts + RP * RB);                           // [LP][8] marks as fp16
   float* km = reinterpret_cast<float*>(Ms + LP * 8);                                  // [LP] min-mask
   unsigned int* red = reinterpret_cast<unsigned int*>(km + LP);                       // [4] tile maxima (K, V, T)
 
@@ -192,101 +225,121 @@ __global__ void __launch_bounds__(((NT + 1) / 2 > 8 ? 8 : (NT + 1) / 2) * 32, MI
   const long long row0 = (long long)b * L;
 
   // ---------------------------------------------------------------- per-sequence operands
+  // MLP constants: asynchronous global -> shared copy, overlapped with everything up to the first barrier wait
   {
-    const uint4* src = reinterpret_cast<const uint4*>(a.mlp_pack);
-    uint4* dst = reinterpret_cast<uint4*>(smem_raw);
-    for (int i = tid; i < LY::PACK_BYTES / 16; i += nthr) dst[i] = __ldg(src + i);
+    const unsigned char* src = reinterpret_cast<const unsigned char*>(a.mlp_pack);
+    for (int i = tid; i < LY::PACK_BYTES / 16; i += nthr) cp_async16(smem_raw + i * 16, src + i * 16);
   }
-  // marks (tf.to_float, temporal.py:311) as fp16, row = [ (2t,2t+1), (2t+8,2t+9) ] for t = 0..3
-  for (int i = tid; i < LP * 4; i += nthr) {
-    const int k = i >> 2, tt = i & 3;
-    uint2 v = make_uint2(0u, 0u);
+  // marks (tf.to_float, temporal.py:311) as fp16; a row holds the two B-fragment words of lane t = 0..3 back to back,
+  // so one 8-byte load is the fragment.  Bytes -> fp16 exactly through 1024 + b (0x6400 | b) - 1024.
+  for (int k = tid; k < LP; k += nthr) {
+    uint4 m = make_uint4(0u, 0u, 0u, 0u);
+    float kv = -INFINITY;
     if (k < L) {
-      const uint8_t* mp = a.marks + (row0 + k) * E;
-      v.x = pack_h2((float)mp[2 * tt], (float)mp[2 * tt + 1]);
-      v.y = pack_h2((float)mp[2 * tt + 8], (float)mp[2 * tt + 9]);
+      m = __ldg(reinterpret_cast<const uint4*>(a.marks + (row0 + k) * E));
+      kv = a.kmask[row0 + k] ? INFINITY : kFillMma;
     }
-    *reinterpret_cast<uint2*>(Ms + k * 8 + 2 * tt) = v;
+    auto h2 = [](uint32_t w, uint32_t sel) {
+      const uint32_t x = __byte_perm(w, 0x64646464u, sel);
+      const __half2 r = __hsub2(*reinterpret_cast<const __half2*>(&x), __floats2half2_rn(1024.f, 1024.f));
+      return *reinterpret_cast<const uint32_t*>(&r);
+    };
+    // word 2t = events (t, 4+t), word 2t+1 = events (8+t, 12+t): k slots 2t, 2t+1, 2t+8, 2t+9 of lane t (see the MLP loop)
+    uint4 w0, w1;
+    w0.x = h2(__byte_perm(m.x, m.y, 0x40u), 0x4140u); w0.y = h2(__byte_perm(m.z, m.w, 0x40u), 0x4140u);
+    w0.z = h2(__byte_perm(m.x, m.y, 0x51u), 0x4140u); w0.w = h2(__byte_perm(m.z, m.w, 0x51u), 0x4140u);
+    w1.x = h2(__byte_perm(m.x, m.y, 0x62u), 0x4140u); w1.y = h2(__byte_perm(m.z, m.w, 0x62u), 0x4140u);
+    w1.z = h2(__byte_perm(m.x, m.y, 0x73u), 0x4140u); w1.w = h2(__byte_perm(m.z, m.w, 0x73u), 0x4140u);
+    *reinterpret_cast<uint4*>(Ms + k * 8) = w0;
+    *reinterpret_cast<uint4*>(Ms + k * 8 + 4) = w1;
+    km[k] = kv;  // min-mask: +inf real key, fill = masked id, -inf = beyond L
   }
-  for (int i = tid; i < LP; i += nthr) km[i] = (i < L) ? (a.kmask[row0 + i] ? INFINITY : kFillMma) : -INFINITY;
+  // rows L..RP-1 of K / V / T stay zero for every head
+  for (int i = tid; i < (RP - L) * (RB / 16) * 3; i += nthr) {
+    const int which = i / ((RP - L) * (RB / 16)), rem = i % ((RP - L) * (RB / 16));
+    *reinterpret_cast<uint4*>(Ks + which * RP * RB + (L + rem / (RB / 16)) * RB + (rem % (RB / 16)) * 16) =
+        make_uint4(0u, 0u, 0u, 0u);
+  }
 
   const float inv_sqrt_dh = 1.0f / sqrtf((float)DH);  // temporal.py:355,422
   const int num_mt = (L + 15) >> 4;
-  constexpr int V4 = DH / 4;
+  // this lane's ldmatrix row addresses (matrix m = lane / 8, row r = lane % 8)
+  const int lm = lane >> 3, lr = lane & 7;
+  const uint32_t ks_addr = (uint32_t)__cvta_generic_to_shared(Ks) + lr * RB + (lm & 1) * 16 + (lm >> 1) * (DH * 2);
+  const uint32_t xoff = ((lm & 1) * 8 + lr) * RB + (lm >> 1) * 16;
+  const uint32_t vs_addr = (uint32_t)__cvta_generic_to_shared(Vs) + xoff;
+  const uint32_t ts_addr = (uint32_t)__cvta_generic_to_shared(Ts) + xoff;
 
   for (int hh = hh0; hh < hh0 + hpc; ++hh) {
     // ---------------------------------------------------------------- stage K, V, T of this head
+    // every global load of the phase is issued before the first use: K/V/T slices, and the Q rows of this warp's
+    // first tile
+    float4 kreg[KI], vreg[KI], treg[KI];
+    float2 xa[KD][2], xb[KD][2];  // raw Q values of rows g / g+8 of a tile (k slots 2t,2t+1 / 2t+8,2t+9 per k16 step)
+    float spa = 0.f, spb = 0.f;   // intervals of the two rows
+    auto load_q = [&](int mt_) {
+      const int qa_ = mt_ * 16 + g, qb_ = qa_ + 8;
+      const long long ra_ = row0 + (qa_ < L ? qa_ : L - 1), rb_ = row0 + (qb_ < L ? qb_ : L - 1);
+#pragma unroll
+      for (int ks = 0; ks < KD; ++ks)
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          xa[ks][hf] = __ldg(reinterpret_cast<const float2*>(a.Q + ra_ * a.ldq + hh * DH + ks * 16 + hf * 8 + 2 * t));
+          xb[ks][hf] = __ldg(reinterpret_cast<const float2*>(a.Q + rb_ * a.ldq + hh * DH + ks * 16 + hf * 8 + 2 * t));
+        }
+      spa = __ldg(a.spans + ra_);
+      spb = __ldg(a.spans + rb_);
+    };
+    if (warp < num_mt) load_q(warp);
+    float mk = 0.f, mv = 0.f, mtt = 0.f;
+#pragma unroll
+    for (int it = 0; it < KI; ++it) {
+      const int i = tid + it * nthr;
+      kreg[it] = vreg[it] = treg[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < L * V4) {
+        const long long r = row0 + i / V4;
+        const int col = hh * DH + (i % V4) * 4;
+        kreg[it] = __ldg(reinterpret_cast<const float4*>(a.K + r * a.ldk + col));
+        vreg[it] = __ldg(reinterpret_cast<const float4*>(a.V + r * a.ldv + col));
+        treg[it] = __ldg(reinterpret_cast<const float4*>(a.T + r * a.ldt + col));
+      }
+    }
     if (tid < 4) red[tid] = 0u;
     __syncthreads();  // previous head fully consumed; red zeroed
-    {
-      float mk = 0.f, mv = 0.f, mtt = 0.f;
-      for (int i = tid; i < L * V4; i += nthr) {
-        const int k = i / V4, j = (i % V4) * 4;
-        const long long r = row0 + k;
-        const float4 kk = __ldg(reinterpret_cast<const float4*>(a.K + r * a.ldk + hh * DH + j));
-        const float4 vv = __ldg(reinterpret_cast<const float4*>(a.V + r * a.ldv + hh * DH + j));
-        const float4 tt = __ldg(reinterpret_cast<const float4*>(a.T + r * a.ldt + hh * DH + j));
-        mk = fmaxf(mk, fmaxf(fmaxf(fabsf(kk.x), fabsf(kk.y)), fmaxf(fabsf(kk.z), fabsf(kk.w))));
-        mv = fmaxf(mv, fmaxf(fmaxf(fabsf(vv.x), fabsf(vv.y)), fmaxf(fabsf(vv.z), fabsf(vv.w))));
-        mtt = fmaxf(mtt, fmaxf(fmaxf(fabsf(tt.x), fabsf(tt.y)), fmaxf(fabsf(tt.z), fabsf(tt.w))));
-      }
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        mk = fmaxf(mk, __shfl_xor_sync(0xffffffffu, mk, o));
-        mv = fmaxf(mv, __shfl_xor_sync(0xffffffffu, mv, o));
-        mtt = fmaxf(mtt, __shfl_xor_sync(0xffffffffu, mtt, o));
-      }
-      if (lane == 0) {
-        atomicMax(&red[0], __float_as_uint(mk));
-        atomicMax(&red[1], __float_as_uint(mv));
-        atomicMax(&red[2], __float_as_uint(mtt));
-      }
+    for (int it = 0; it < KI; ++it) {
+      mk = absmax4(mk, kreg[it]);
+      mv = absmax4(mv, vreg[it]);
+      mtt = absmax4(mtt, treg[it]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mk = fmaxf(mk, __shfl_xor_sync(0xffffffffu, mk, o));
+      mv = fmaxf(mv, __shfl_xor_sync(0xffffffffu, mv, o));
+      mtt = fmaxf(mtt, __shfl_xor_sync(0xffffffffu, mtt, o));
+    }
+    if (lane == 0) {
+      atomicMax(&red[0], __float_as_uint(mk));
+      atomicMax(&red[1], __float_as_uint(mv));
+      atomicMax(&red[2], __float_as_uint(mtt));
     }
     __syncthreads();
     float sk, isk, sv, isv, st, ist;
     pow2_scale(__uint_as_float(red[0]), sk, isk);
     pow2_scale(__uint_as_float(red[1]), sv, isv);
     pow2_scale(__uint_as_float(red[2]), st, ist);
-    // K: [key][k16 block][lane t]{hi(4t,4t+1), hi(4t+2,4t+3), lo, lo}: k slots (2t,2t+1,2t+8,2t+9) <-> dims 4t..4t+3
-    for (int i = tid; i < LP * V4; i += nthr) {
-      const int k = i / V4, j4 = i % V4;
-      uint4 v = make_uint4(0u, 0u, 0u, 0u);
-      if (k < L) {
-        const float4 kk = __ldg(reinterpret_cast<const float4*>(a.K + (row0 + k) * a.ldk + hh * DH + j4 * 4));
-        split2(kk.x * sk, kk.y * sk, v.x, v.z);
-        split2(kk.z * sk, kk.w * sk, v.y, v.w);
-      }
-      *reinterpret_cast<uint4*>(Ks + k * SKW + (j4 >> 2) * 16 + (j4 & 3) * 4) = v;
-    }
-    // V^T, T^T: [dim][16-key block j][lane t]{hi(keys 2t,2t+1), hi(keys 2t+8,2t+9), lo, lo}; one thread packs the
-    // key pair (2p, 2p+1) of four dims
-    for (int i = tid; i < NB * 8 * V4; i += nthr) {
-      const int p = i / V4, dg = i % V4;
-      const int k0 = 2 * p, j = k0 >> 4, s = k0 & 15;          // s even
-      const int word = j * 16 + ((s & 7) >> 1) * 4 + (s >> 3);  // hi word; lo word is +2
-      float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0, t0 = v0, t1 = v0;
-      if (k0 < L) {
-        v0 = __ldg(reinterpret_cast<const float4*>(a.V + (row0 + k0) * a.ldv + hh * DH + dg * 4));
-        t0 = __ldg(reinterpret_cast<const float4*>(a.T + (row0 + k0) * a.ldt + hh * DH + dg * 4));
-      }
-      if (k0 + 1 < L) {
-        v1 = __ldg(reinterpret_cast<const float4*>(a.V + (row0 + k0 + 1) * a.ldv + hh * DH + dg * 4));
-        t1 = __ldg(reinterpret_cast<const float4*>(a.T + (row0 + k0 + 1) * a.ldt + hh * DH + dg * 4));
-      }
-      const float va[4] = {v0.x, v0.y, v0.z, v0.w}, vb[4] = {v1.x, v1.y, v1.z, v1.w};
-      const float ta[4] = {t0.x, t0.y, t0.z, t0.w}, tb[4] = {t1.x, t1.y, t1.z, t1.w};
+    // rows [key]{hi[DH] | lo[DH] | pad}: natural dim order, read with ldmatrix (K) / ldmatrix.trans (V, T)
 #pragma unroll
-      for (int e0 = 0; e0 < 4; ++e0) {
-        const int e = (e0 + dg) & 3;  // rotate so the four dim groups do not hit the same banks
-        uint32_t hi, lo;
-        split2(va[e] * sv, vb[e] * sv, hi, lo);
-        Vt[(dg * 4 + e) * SVW + word] = hi;
-        Vt[(dg * 4 + e) * SVW + word + 2] = lo;
-        split2(ta[e] * st, tb[e] * st, hi, lo);
-        Tt[(dg * 4 + e) * SVW + word] = hi;
-        Tt[(dg * 4 + e) * SVW + word + 2] = lo;
+    for (int it = 0; it < KI; ++it) {
+      const int i = tid + it * nthr;
+      if (i < L * V4) {
+        const int k = i / V4, d0 = (i % V4) * 4;
+        put4(Ks + k * RB, d0, DH * 2, kreg[it], sk);
+        put4(Vs + k * RB, d0, DH * 2, vreg[it], sv);
+        put4(Ts + k * RB, d0, DH * 2, treg[it], st);
       }
     }
+    cp_async_wait_all();
     __syncthreads();
     const float isw = misc[0];
     const float zscale = ist * isw;  // MLP accumulator -> -z log2(e)
@@ -300,15 +353,15 @@ __global__ void __launch_bounds__(((NT + 1) / 2 > 8 ? 8 : (NT + 1) / 2) * 32, MI
       float iqa, iqb;
       uint32_t qh[KD][4], ql[KD][4];
       {
-        float4 xa[KD], xb[KD];
+        if (mt != warp) load_q(mt);  // the first tile's rows were requested before the staging barriers
         float ma = 0.f, mb = 0.f;
 #pragma unroll
-        for (int ks = 0; ks < KD; ++ks) {
-          xa[ks] = __ldg(reinterpret_cast<const float4*>(a.Q + ra * a.ldq + hh * DH + ks * 16 + 4 * t));
-          xb[ks] = __ldg(reinterpret_cast<const float4*>(a.Q + rb * a.ldq + hh * DH + ks * 16 + 4 * t));
-          ma = fmaxf(ma, fmaxf(fmaxf(fabsf(xa[ks].x), fabsf(xa[ks].y)), fmaxf(fabsf(xa[ks].z), fabsf(xa[ks].w))));
-          mb = fmaxf(mb, fmaxf(fmaxf(fabsf(xb[ks].x), fabsf(xb[ks].y)), fmaxf(fabsf(xb[ks].z), fabsf(xb[ks].w))));
-        }
+        for (int ks = 0; ks < KD; ++ks)
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            ma = fmaxf(ma, fmaxf(fabsf(xa[ks][hf].x), fabsf(xa[ks][hf].y)));
+            mb = fmaxf(mb, fmaxf(fabsf(xb[ks][hf].x), fabsf(xb[ks][hf].y)));
+          }
         ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, 1));
         ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, 2));
         mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, 1));
@@ -318,10 +371,10 @@ __global__ void __launch_bounds__(((NT + 1) / 2 > 8 ? 8 : (NT + 1) / 2) * 32, MI
         pow2_scale(mb, sqb, iqb);
 #pragma unroll
         for (int ks = 0; ks < KD; ++ks) {
-          split2(xa[ks].x * sqa, xa[ks].y * sqa, qh[ks][0], ql[ks][0]);
-          split2(xb[ks].x * sqb, xb[ks].y * sqb, qh[ks][1], ql[ks][1]);
-          split2(xa[ks].z * sqa, xa[ks].w * sqa, qh[ks][2], ql[ks][2]);
-          split2(xb[ks].z * sqb, xb[ks].w * sqb, qh[ks][3], ql[ks][3]);
+          split2(xa[ks][0].x * sqa, xa[ks][0].y * sqa, qh[ks][0], ql[ks][0]);
+          split2(xb[ks][0].x * sqb, xb[ks][0].y * sqb, qh[ks][1], ql[ks][1]);
+          split2(xa[ks][1].x * sqa, xa[ks][1].y * sqa, qh[ks][2], ql[ks][2]);
+          split2(xb[ks][1].x * sqb, xb[ks][1].y * sqb, qh[ks][3], ql[ks][3]);
         }
       }
       // ---- S = Q K^T  (accumulators P[nt][c]: rows g / g+8, keys nt*8 + 2t + (c&1)); four key tiles in flight
@@ -332,19 +385,19 @@ __global__ void __launch_bounds__(((NT + 1) / 2 > 8 ? 8 : (NT + 1) / 2) * 32, MI
       for (int n0 = 0; n0 < NT; n0 += 4) {
 #pragma unroll
         for (int ks = 0; ks < KD; ++ks) {
-          uint4 kb[4];
+          uint32_t kb[4][4];  // {b0 hi, b1 hi, b0 lo, b1 lo}
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            if (n0 + j < NT) kb[j] = *reinterpret_cast<const uint4*>(Ks + ((n0 + j) * 8 + g) * SKW + ks * 16 + t * 4);
+            if (n0 + j < NT) ldsm_x4(kb[j], ks_addr + (n0 + j) * 8 * RB + ks * 32);
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            if (n0 + j < NT) mma_f16(P[n0 + j], ql[ks], kb[j].x, kb[j].y);
+            if (n0 + j < NT) mma_f16(P[n0 + j], ql[ks], kb[j][0], kb[j][1]);
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            if (n0 + j < NT) mma_f16(P[n0 + j], qh[ks], kb[j].z, kb[j].w);
+            if (n0 + j < NT) mma_f16(P[n0 + j], qh[ks], kb[j][2], kb[j][3]);
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            if (n0 + j < NT) mma_f16(P[n0 + j], qh[ks], kb[j].x, kb[j].y);
+            if (n0 + j < NT) mma_f16(P[n0 + j], qh[ks], kb[j][0], kb[j][1]);
         }
       }
       // ---- scale, key mask, causal mask, softmax in the log2 domain (see attn_mma.cuh)
@@ -391,9 +444,8 @@ __global__ void __launch_bounds__(((NT + 1) / 2 > 8 ? 8 : (NT + 1) / 2) * 32, MI
       }
       // ---- H = P T : accumulator = H * 2^14 * scale(T); |H * scale(T)| < 2^15 because rows of P sum to 1
       float H[ND][4];
-      pv_product16<DH, NT>(P, Tt, SVW, H, g, t);
+      pv_product16<DH, NT>(P, ts_addr, H);
       // ---- intensity MLP: Z = sigmoid([H, span] W1 + b1); dot with w per event (temporal.py:287-305)
-      const float spa = a.spans[ra], spb = a.spans[rb];
       uint32_t hh_[KD][4], hl_[KD][4];
 #pragma unroll
       for (int ks = 0; ks < KD; ++ks) {
@@ -403,11 +455,24 @@ __global__ void __launch_bounds__(((NT + 1) / 2 > 8 ? 8 : (NT + 1) / 2) * 32, MI
         split2(H[2 * ks + 1][0] * k2m14, H[2 * ks + 1][1] * k2m14, hh_[ks][2], hl_[ks][2]);
         split2(H[2 * ks + 1][2] * k2m14, H[2 * ks + 1][3] * k2m14, hh_[ks][3], hl_[ks][3]);
       }
-      float lsa[E], lsb[E];  // per-event dot products for rows qa / qb (full sums after the quad reduce)
-      {
-        float pa = 0.f, pb = 0.f;
+      // Events are processed four at a time in a ROLLED loop (code size: the instruction cache is shared by 28 warps in
+      // different phases).  Within a group each lane accumulates its columns' share of the four per-event dot
+      // products; a 4x4 transpose-reduce over the quad (3 shuffles per row) leaves lane t with the full sum of event
+      // 4*eg + t, which it turns into lam right away.  So after the loop lane t owns the events t, 4+t, 8+t, 12+t:
+      // these ARE the k slots 2t, 2t+1, 2t+8, 2t+9 of its A-fragment registers (the marks rows are staged in the same
+      // slot order), and no per-event array is ever live.
+      // lam_e = s_e log(1 + exp(x / s_e))  (temporal.py:305-306)
+      float va[4], vb[4];
 #pragma unroll
-        for (int tg = 0; tg < MT; tg += 4) {
+      for (int i = 0; i < 4; ++i) va[i] = vb[i] = 0.f;
+#pragma unroll 1
+      for (int eg = 0; eg < E / 4; ++eg) {
+        float pa[4] = {0.f, 0.f, 0.f, 0.f}, pb[4] = {0.f, 0.f, 0.f, 0.f};
+        const uint32_t* w1g = W1t + (size_t)(eg * 4 * ND * 8 + g) * SKW + t * 4;
+        const float4* bwg = bw + eg * 4 * ND * 4 + t;
+        const float* wvg = wv + eg * 4 * ND * 8 + 2 * t;
+#pragma unroll
+        for (int tq = 0; tq < ND; ++tq) {  // 4 tiles of 8 columns at a time
           float z[4][4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) z[j][0] = z[j][1] = z[j][2] = z[j][3] = 0.f;
@@ -416,7 +481,7 @@ __global__ void __launch_bounds__(((NT + 1) / 2 > 8 ? 8 : (NT + 1) / 2) * 32, MI
             uint4 wb[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              wb[j] = *reinterpret_cast<const uint4*>(W1t + ((tg + j) * 8 + g) * SKW + ks * 16 + t * 4);
+              wb[j] = *reinterpret_cast<const uint4*>(w1g + (tq * 4 + j) * 8 * SKW + ks * 16);
 #pragma unroll
             for (int j = 0; j < 4; ++j) mma_f16(z[j], hl_[ks], wb[j].x, wb[j].y);
 #pragma unroll
@@ -426,53 +491,52 @@ __global__ void __launch_bounds__(((NT + 1) / 2 > 8 ? 8 : (NT + 1) / 2) * 32, MI
           }
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const int tt = tg + j;
-            const float4 bb = bw[tt * 4 + t];  // {b1[c0], b1[c0+1], wsp[c0], wsp[c0+1]}, c0 = tt*8 + 2t
-            const float2 we = *reinterpret_cast<const float2*>(wv + tt * 8 + 2 * t);
+            const int tl = tq * 4 + j;         // tile inside the group; its event is tl / ND
+            const float4 bb = bwg[tl * 4];     // {b1[c0], b1[c0+1], wsp[c0], wsp[c0+1]}, c0 = tile*8 + 2t
+            const float2 we = *reinterpret_cast<const float2*>(wvg + tl * 8);
             const float z0 = fmaf(z[j][0], zscale, fmaf(spa, bb.z, bb.x)), z1 = fmaf(z[j][1], zscale, fmaf(spa, bb.w, bb.y));
             const float z2 = fmaf(z[j][2], zscale, fmaf(spb, bb.z, bb.x)), z3 = fmaf(z[j][3], zscale, fmaf(spb, bb.w, bb.y));
             // z* hold -z*log2(e): sigmoid = 1 / (1 + 2^(z*))   (tf.nn.sigmoid, temporal.py:290)
-            pa = fmaf(rcp_approx(1.f + ex2_approx(z0)), we.x, pa);
-            pa = fmaf(rcp_approx(1.f + ex2_approx(z1)), we.y, pa);
-            pb = fmaf(rcp_approx(1.f + ex2_approx(z2)), we.x, pb);
-            pb = fmaf(rcp_approx(1.f + ex2_approx(z3)), we.y, pb);
-            if ((tt % ND) == ND - 1) {  // event complete: reduce over the quad (columns live across lanes t)
-              pa += __shfl_xor_sync(0xffffffffu, pa, 1);
-              pa += __shfl_xor_sync(0xffffffffu, pa, 2);
-              pb += __shfl_xor_sync(0xffffffffu, pb, 1);
-              pb += __shfl_xor_sync(0xffffffffu, pb, 2);
-              lsa[tt / ND] = pa;
-              lsb[tt / ND] = pb;
-              pa = 0.f;
-              pb = 0.f;
-            }
+            pa[tl / ND] = fmaf(rcp_approx(1.f + ex2_approx(z0)), we.x, pa[tl / ND]);
+            pa[tl / ND] = fmaf(rcp_approx(1.f + ex2_approx(z1)), we.y, pa[tl / ND]);
+            pb[tl / ND] = fmaf(rcp_approx(1.f + ex2_approx(z2)), we.x, pb[tl / ND]);
+            pb[tl / ND] = fmaf(rcp_approx(1.f + ex2_approx(z3)), we.y, pb[tl / ND]);
           }
         }
+        // 4x4 transpose-reduce over the quad: lane t ends with the sum over lanes of p[t]
+        const bool odd = (t & 1) != 0, up = (t & 2) != 0;
+        float xa, xb;
+        {
+          const float r0 = __shfl_xor_sync(0xffffffffu, odd ? pa[0] : pa[1], 1);
+          const float r1 = __shfl_xor_sync(0xffffffffu, odd ? pa[2] : pa[3], 1);
+          const float w0 = (odd ? pa[1] : pa[0]) + r0, w1 = (odd ? pa[3] : pa[2]) + r1;
+          xa = (up ? w1 : w0) + __shfl_xor_sync(0xffffffffu, up ? w0 : w1, 2);
+        }
+        {
+          const float r0 = __shfl_xor_sync(0xffffffffu, odd ? pb[0] : pb[1], 1);
+          const float r1 = __shfl_xor_sync(0xffffffffu, odd ? pb[2] : pb[3], 1);
+          const float w0 = (odd ? pb[1] : pb[0]) + r0, w1 = (odd ? pb[3] : pb[2]) + r1;
+          xb = (up ? w1 : w0) + __shfl_xor_sync(0xffffffffu, up ? w0 : w1, 2);
+        }
+        const int ev = eg * 4 + t;
+        const float s = sc[ev];
+        // naive softplus like the reference (overflows to inf for x/s > 88.7, Q6), on the fast exp2/log2 units
+        const float rs = rcp_approx(s) * kLog2e, sl = s * 0.69314718055994531f;
+        const float la_ = sl * lg2_approx(1.f + ex2_approx(xa * rs));
+        const float lb_ = sl * lg2_approx(1.f + ex2_approx(xb * rs));
+        if (a.lam) {
+          if (qa < L) a.lam[(((long long)hh * B + b) * L + qa) * E + ev] = la_;  // head-major, temporal.py:413
+          if (qb < L) a.lam[(((long long)hh * B + b) * L + qb) * E + ev] = lb_;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          va[i] = (eg == i) ? la_ : va[i];
+          vb[i] = (eg == i) ? lb_ : vb[i];
+        }
       }
-      // ---- lam_e = s_e log(1 + exp(x / s_e))  (temporal.py:305-306); lane t owns events 2t, 2t+1, 2t+8, 2t+9
-      // (= the k slots of its A fragment registers)
       uint32_t lh[4], ll[4];
       float isla, islb, sla, slb;
       {
-        float va[4], vb[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int eb = (i & 1) + (i >> 1) * 8;  // event of lane 0; lane t adds 2t
-          float xa = lsa[eb], xb = lsb[eb];
-          if (t == 1) { xa = lsa[eb + 2]; xb = lsb[eb + 2]; }
-          if (t == 2) { xa = lsa[eb + 4]; xb = lsb[eb + 4]; }
-          if (t == 3) { xa = lsa[eb + 6]; xb = lsb[eb + 6]; }
-          const int ev = eb + 2 * t;
-          const float s = sc[ev];
-          // naive softplus like the reference (overflows to inf for x/s > 88.7, Q6), on the fast exp2/log2 units
-          const float rs = rcp_approx(s) * kLog2e, sl = s * 0.69314718055994531f;
-          va[i] = sl * lg2_approx(1.f + ex2_approx(xa * rs));
-          vb[i] = sl * lg2_approx(1.f + ex2_approx(xb * rs));
-          if (a.lam) {
-            if (qa < L) a.lam[(((long long)hh * B + b) * L + qa) * E + ev] = va[i];  // head-major, temporal.py:413
-            if (qb < L) a.lam[(((long long)hh * B + b) * L + qb) * E + ev] = vb[i];
-          }
-        }
         float ma2 = fmaxf(fmaxf(fabsf(va[0]), fabsf(va[1])), fmaxf(fabsf(va[2]), fabsf(va[3])));
         float mb2 = fmaxf(fmaxf(fabsf(vb[0]), fabsf(vb[1])), fmaxf(fabsf(vb[2]), fabsf(vb[3])));
         ma2 = fmaxf(ma2, __shfl_xor_sync(0xffffffffu, ma2, 1));
@@ -481,13 +545,22 @@ __global__ void __launch_bounds__(((NT + 1) / 2 > 8 ? 8 : (NT + 1) / 2) * 32, MI
         mb2 = fmaxf(mb2, __shfl_xor_sync(0xffffffffu, mb2, 2));
         pow2_scale(ma2, sla, isla);
         pow2_scale(mb2, slb, islb);
-        split2(va[0] * sla, va[1] * sla, lh[0], ll[0]);
-        split2(vb[0] * slb, vb[1] * slb, lh[1], ll[1]);
-        split2(va[2] * sla, va[3] * sla, lh[2], ll[2]);
-        split2(vb[2] * slb, vb[3] * slb, lh[3], ll[3]);
+        split2(va[0] * sla, va[1] * sla, lh[0], ll[0]);   // a0: row g,   k slots 2t, 2t+1   = events t, 4+t
+        split2(vb[0] * slb, vb[1] * slb, lh[1], ll[1]);   // a1: row g+8
+        split2(va[2] * sla, va[3] * sla, lh[2], ll[2]);   // a2: row g,   k slots 2t+8, 2t+9 = events 8+t, 12+t
+        split2(vb[2] * slb, vb[3] * slb, lh[3], ll[3]);   // a3: row g+8
       }
       // ---- G = lam M^T (marks exact in fp16: 2 MMAs), set_diag, gate: P <- G o P   (temporal.py:309-313,438-441)
       // accumulators carry the row scale of lam, so a forced diagonal of 1 is that scale
+      float2 res_a[ND], res_b[ND];  // residual rows, requested here so the gate and (G o P) V hide the latency
+#pragma unroll
+      for (int n = 0; n < ND; ++n) {
+        res_a[n] = res_b[n] = make_float2(0.f, 0.f);
+        if (a.R) {
+          res_a[n] = __ldg(reinterpret_cast<const float2*>(a.R + ra * a.ldr + hh * DH + n * 8 + 2 * t));
+          res_b[n] = __ldg(reinterpret_cast<const float2*>(a.R + rb * a.ldr + hh * DH + n * 8 + 2 * t));
+        }
+      }
       float ga = 0.f, gb = 0.f;  // row maxima of G o P
 #pragma unroll
       for (int n0 = 0; n0 < NT; n0 += 4) {
@@ -531,7 +604,7 @@ __global__ void __launch_bounds__(((NT + 1) / 2 > 8 ? 8 : (NT + 1) / 2) * 32, MI
       }
       // ---- O = (G o P) V : accumulator = O * 2^14 * scale(lam row) * scale(G o P row) * scale(V)
       float O[ND][4];
-      pv_product16<DH, NT>(P, Vt, SVW, O, g, t);
+      pv_product16<DH, NT>(P, vs_addr, O);
       constexpr float k2m14 = 1.0f / 16384.f;
       const float fa = isv * isga, fb = isv * isgb;
       const float fa2 = k2m14 * isla, fb2 = k2m14 * islb;
@@ -541,18 +614,12 @@ __global__ void __launch_bounds__(((NT + 1) / 2 > 8 ? 8 : (NT + 1) / 2) * 32, MI
         const int col = hh * DH + n * 8 + 2 * t;
         if (qa < L) {
           float2 o = make_float2(O[n][0] * fa * fa2, O[n][1] * fa * fa2);
-          if (a.R) {
-            const float2 r = *reinterpret_cast<const float2*>(a.R + (row0 + qa) * a.ldr + col);
-            o.x += r.x; o.y += r.y;
-          }
+          o.x += res_a[n].x; o.y += res_a[n].y;
           *reinterpret_cast<float2*>(a.O + (row0 + qa) * a.ldo + col) = o;
         }
         if (qb < L) {
           float2 o = make_float2(O[n][2] * fb * fb2, O[n][3] * fb * fb2);
-          if (a.R) {
-            const float2 r = *reinterpret_cast<const float2*>(a.R + (row0 + qb) * a.ldr + col);
-            o.x += r.x; o.y += r.y;
-          }
+          o.x += res_b[n].x; o.y += res_b[n].y;
           *reinterpret_cast<float2*>(a.O + (row0 + qb) * a.ldo + col) = o;
         }
       }
@@ -560,13 +627,15 @@ __global__ void __launch_bounds__(((NT + 1) / 2 > 8 ? 8 : (NT + 1) / 2) * 32, MI
   }
 }
 
-template <int DH, int NT, int MINB>
+template <int DH, int NT, int MAXREG>
 int launch_f16_t(const AttnArgs& a, int hpc, cudaStream_t st) {
   using LY = F16Layout<DH>;
   const size_t smem = LY::smem_bytes(NT);
   if (smem > 227 * 1024) return 1;
-  auto kern = attention_f16_kernel<DH, NT, MINB>;
+  auto kern = attention_f16_kernel<DH, NT, MAXREG>;
   EDGL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // several ~50 KB CTAs per SM: ask for the largest shared-memory carve-out, or the driver's default split caps residency
+  EDGL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   int warps = (a.L + 15) / 16;
   if (warps > 8) warps = 8;
   kern<<<(unsigned)(a.B * (a.h / hpc)), warps * 32, smem, st>>>(a, hpc);
@@ -594,20 +663,26 @@ int launch_attention_f16_pack(const float* int_w, const float* int_b, const floa
 int launch_attention_f16(const AttnArgs& a, cudaStream_t st) {
   const int dh = a.d / a.h;
   if (dh != 16 || a.E != 16 || !a.mlp_pack || a.L > 208) return 1;
+  if (reinterpret_cast<uintptr_t>(a.marks) & 15) return 1;  // mark rows are read as 16-byte words
   static const int hpc_env = [] {
     const char* e = getenv("EDGL_ATTN_HPC");
     return e ? atoi(e) : 1;
   }();
-  static const int occ_env = [] {
-    const char* e = getenv("EDGL_ATTN_OCC");
-    return e ? atoi(e) : 2;
+  static const int occ_env = [] {  // registers per thread of the L <= 104 instantiation (tuning knob)
+    const char* e = getenv("EDGL_ATTN_REGS");
+    return e ? atoi(e) : 96;
   }();
   int hpc = hpc_env;
   if (hpc < 1 || a.h % hpc != 0) hpc = 1;
-  if (a.L <= 32) return launch_f16_t<16, 4, 2>(a, hpc, st);
-  if (a.L <= 104) return occ_env == 3 ? launch_f16_t<16, 13, 3>(a, hpc, st) : launch_f16_t<16, 13, 2>(a, hpc, st);
-  if (a.L <= 128) return launch_f16_t<16, 16, 2>(a, hpc, st);
-  return launch_f16_t<16, 26, 1>(a, hpc, st);
+  if (a.L <= 32) return launch_f16_t<16, 4, 128>(a, hpc, st);
+  if (a.L <= 104) {
+    if (occ_env == 72) return launch_f16_t<16, 13, 72>(a, hpc, st);
+    if (occ_env == 80) return launch_f16_t<16, 13, 80>(a, hpc, st);
+    if (occ_env == 128) return launch_f16_t<16, 13, 128>(a, hpc, st);
+    return launch_f16_t<16, 13, 96>(a, hpc, st);
+  }
+  if (a.L <= 128) return launch_f16_t<16, 16, 128>(a, hpc, st);
+  return launch_f16_t<16, 26, 255>(a, hpc, st);
 }
 
 }  // namespace edgl

@@ -376,7 +376,7 @@ int launch_attention(const AttnArgs& a, cudaStream_t st) {
   // CUDA-core kernel below (same results to fp32 rounding; used by the parity tests to cover both)
   static const char mode = [] {
     const char* e = getenv("EDGL_ATTN");
-    return e ? e[0] : 'm';
+    return e ? e[0] : 'd';
   }();
   const bool force_simt = mode == 's';
   // EDGL_ATTN=tc: the tcgen05 / TMEM kernel (attn_tc.cu; dh = 16, E = 16, L <= 128).  It passes the same
@@ -387,8 +387,9 @@ int launch_attention(const AttnArgs& a, cudaStream_t st) {
     const int r = launch_attention_tc(a, st);
     if (r <= 0) return r;
   }
-  // EDGL_ATTN=f16: the scaled 3xFP16 mma.sync kernel (attn_f16.cu; dh = 16, E = 16, L <= 208)
-  if (mode == 'f') {
+  // default (and EDGL_ATTN=f16): the scaled 3xFP16 mma.sync kernel (attn_f16.cu; dh = 16, E = 16, L <= 208).
+  // EDGL_ATTN=mma selects the 3xTF32 mma.sync kernel for every shape, as before.
+  if (mode == 'f' || mode == 'd') {
     const int r = launch_attention_f16(a, st);
     if (r <= 0) return r;
   }

@@ -12,13 +12,14 @@ namespace edgl {
 __device__ __forceinline__ float2 ld2(const float* p) { return *reinterpret_cast<const float2*>(p); }
 __device__ __forceinline__ void st2(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
 
-// rows are (b,l) flattened. blockDim = 128 (4 warps = 4 rows).
+// One warp per (b,l) row; blockDim = 128 (4 warps = 4 consecutive positions of one sequence), grid = (B, ceil(L/4)):
+// the kernel is issue-bound (accurate sincos of 64 arguments per row), so (b,l) come from the block index instead of
+// a 64-bit division and the mark histogram is done with byte-compare SIMD on the 16-byte mark row.
 __global__ void __launch_bounds__(128) embed_kernel(EmbedArgs a, float sqrt_d) {
   const int lane = threadIdx.x & 31;
-  const long long row = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
-  const long long rows = (long long)a.B * a.L;
-  if (row >= rows) return;
-  const int b = (int)(row / a.L), l = (int)(row % a.L);
+  const int b = blockIdx.x, l = blockIdx.y * 4 + (threadIdx.x >> 5);
+  if (l >= a.L) return;
+  const long long row = (long long)b * a.L + l;
   const int d = a.d, E = a.E, half = d >> 1;
   const long long id = a.ids[row];
   const bool id_ok = id > 0 && id < a.num_rows;  // id 0 = zero-padded row (coding.py:56-57)
@@ -77,11 +78,25 @@ __global__ void __launch_bounds__(128) embed_kernel(EmbedArgs a, float sqrt_d) {
   if (a.Xa && a.model == 0) {
     // histogram of mark values: cnt[v] = #{e : marks[e] == v}; the mark code is cnt @ mark_embs_zp,
     // so the block-0 QKVT dense sees it through a [E,4d] folded kernel (api.cu commit()).
-    for (int v = lane; v < E; v += 32) {
-      int c = 0;
-      if (mid_ok)
-        for (int e = 0; e < E; ++e) c += (mrow[e] == v);
-      a.Xa[row * a.ldxa + d + v] = (float)c;
+    if (E == 16 && (reinterpret_cast<uintptr_t>(a.mark_table8) & 15) == 0) {
+      // the whole mark row is one 16-byte word (same address in every lane: a broadcast load); lane v counts the
+      // bytes equal to v with a per-byte compare (0xff per hit -> popcount / 8)
+      const uint4 m = mid_ok ? *reinterpret_cast<const uint4*>(mrow) : make_uint4(0u, 0u, 0u, 0u);
+      if (lane < 16) {
+        const unsigned int vv = (unsigned int)lane * 0x01010101u;
+        int c = __popc(__vcmpeq4(m.x, vv)) + __popc(__vcmpeq4(m.y, vv)) + __popc(__vcmpeq4(m.z, vv)) +
+                __popc(__vcmpeq4(m.w, vv));
+        c >>= 3;
+        if (!mid_ok) c = 0;  // TF-GPU semantics for an out-of-range id: zero rows everywhere
+        a.Xa[row * a.ldxa + d + lane] = (float)c;
+      }
+    } else {
+      for (int v = lane; v < E; v += 32) {
+        int c = 0;
+        if (mid_ok)
+          for (int e = 0; e < E; ++e) c += (mrow[e] == v);
+        a.Xa[row * a.ldxa + d + v] = (float)c;
+      }
     }
   }
 }
@@ -91,7 +106,8 @@ int launch_embed(const EmbedArgs& a, cudaStream_t st) {
   EDGL_REQUIRE(a.L >= 2 || a.model == 1, "EasyDGL needs seq_len >= 2 (spans, EasyDGL.py:73-74)");
   const long long rows = (long long)a.B * a.L;
   if (rows == 0) return 0;
-  embed_kernel<<<cdiv(rows, 4), 128, 0, st>>>(a, (float)sqrt((double)a.d));
+  EDGL_REQUIRE(cdiv(a.L, 4) <= 65535, "embed: sequence length %d exceeds the grid limit", a.L);
+  embed_kernel<<<dim3((unsigned)a.B, (unsigned)cdiv(a.L, 4)), 128, 0, st>>>(a, (float)sqrt((double)a.d));
   EDGL_LAUNCH_CHECK();
   return 0;
 }

@@ -323,9 +323,12 @@ def run_ours(args):
             roof = {"kernel": dom, "bound": "tensor", "achieved": round(ach, 3), "peak": tf_peak, "unit": "TFLOP/s",
                     "frac": round(ach / tf_peak, 5), "traffic": traffic, "peak_source": peak_src,
                     "note": "algorithmic fp32 FLOPs of the kernel / CUDA-event time; peak is the measured dense bf16 "
-                            "rate. The kernel runs 3xTF32 (3 tensor-core products per algorithmic product at half "
-                            "the bf16 rate: ceiling = peak/6) because the top-K parity bar needs fp32-level "
-                            "accuracy (DESIGN.md); traffic = ncu dram bytes/launch (profiles/traffic.json)"}
+                            "tcgen05 rate. The attention core runs a scaled 3xFP16 split on mma.sync (3 tensor-core "
+                            "products per algorithmic product: tensor ceiling = peak/3 even on tcgen05) because the "
+                            "top-K parity bar needs fp32-level accuracy, and it is bound by issue slots and the MUFU "
+                            "(256 sigmoids per row and head), not by the tensor pipe: see stages[*] / "
+                            "profiles/traffic.json for issue, XU and tensor pipe utilisation (DESIGN.md 4); "
+                            "traffic = ncu dram bytes/launch (profiles/traffic.json)"}
         elif dom in by:
             hb = peaks.get("hbm_gbs", 6650.0)
             ach = by[dom] / ((prof[dom][0] / prof[dom][1]) * 1e-3) / 1e9

@@ -123,6 +123,17 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// 16 TMEM lanes x 16 columns as an MMA-accumulator-style fragment: thread (g = lane/4, t = lane%4) gets, for each
+// 8-column group j, r[4j], r[4j+1] = row g, columns 8j + 2t, 2t+1 and r[4j+2], r[4j+3] = row g + 8, same columns.
+// A quad then owns 32 contiguous bytes of a row: rows can be stored straight from registers, sector by sector.
+__device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 struct Params {
   float* C; int ldc;
   int M, N, K;
@@ -132,6 +143,7 @@ struct Params {
   int act;
   int col0_bias_only;  // tied zero-padded table: column 0 is exactly the bias (coding.py:56-57)
   int ntn, num_tiles, kblocks;
+  int epi_direct;  // epilogue stores rows straight from TMEM fragments (no shared-memory transpose)
   int has_blo;  // W_lo = W - tf32(W) is pre-computed in global memory (weights are constant after commit): TMA brings
                 // it in like W and the splitter warps only split the activations
   long long* dbg;  // optional [gridDim][8] cycle counters (EDGL_TC_DEBUG), else null
@@ -326,6 +338,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           if (pr >= p.pperiod) pr -= p.pperiod;
         }
       }
+      int pbd[4] = {0, 0, 0, 0};  // direct path: periodic-bias offsets of rows m0 + q*32 + {0,8,16,24} + lane/4
+      if (p.pbias && p.epi_direct) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) pbd[i] = ((m0 + q * 32 + i * 8 + (lane >> 2)) % p.pperiod) * p.N;
+      }
       const long long t0 = clock64();
       mbar_wait(&tfull[acc], (tcount >> 1) & 1);
       const long long t1 = clock64();
@@ -333,6 +350,44 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       tc_fence_after();
 #pragma unroll 1
       for (int c0 = half * CW; c0 < BN; c0 += 2 * CW) {
+        if (p.epi_direct && all_al && n0 + c0 + CW <= p.N) {
+          // ---- direct path: two 16-row halves; every store instruction writes 8 rows x one 32-byte sector
+          const int g = lane >> 2, t2 = (lane & 3) * 2;
+#pragma unroll
+          for (int hr = 0; hr < 2; ++hr) {
+            uint32_t r8[8];
+            tmem_ld_16x256b_x2(tmem_base + acc * BN + c0 + ((uint32_t)(q * 32 + hr * 16) << 16), r8);
+            float2 add[2][2], res[2][2];
+#pragma unroll
+            for (int h8 = 0; h8 < 2; ++h8)
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                const int row = m0 + q * 32 + hr * 16 + h8 * 8 + g, col = n0 + c0 + 8 * j + t2;
+                float2 a2 = p.bias ? *reinterpret_cast<const float2*>(p.bias + col) : make_float2(0.f, 0.f);
+                if (p.pbias) {
+                  const float2 pp = *reinterpret_cast<const float2*>(p.pbias + pbd[hr * 2 + h8] + col);
+                  a2.x += pp.x; a2.y += pp.y;
+                }
+                add[h8][j] = a2;
+                res[h8][j] = (p.R && row < p.M) ? *reinterpret_cast<const float2*>(p.R + (size_t)row * p.ldr + col)
+                                                : make_float2(0.f, 0.f);
+              }
+#pragma unroll
+            for (int h8 = 0; h8 < 2; ++h8)
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                const int row = m0 + q * 32 + hr * 16 + h8 * 8 + g, col = n0 + c0 + 8 * j + t2;
+                float2 v = make_float2(__uint_as_float(r8[4 * j + 2 * h8]), __uint_as_float(r8[4 * j + 2 * h8 + 1]));
+                if (p.col0_bias_only && col == 0) v.x = 0.f;
+                v.x += add[h8][j].x; v.y += add[h8][j].y;
+                if (ACT == ACT_GELU) { v.x = gelu_erf_tc(v.x); v.y = gelu_erf_tc(v.y); }
+                if (ACT == ACT_RELU) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); }
+                v.x += res[h8][j].x; v.y += res[h8][j].y;
+                if (row < p.M) *reinterpret_cast<float2*>(p.C + (size_t)row * p.ldc + col) = v;
+              }
+          }
+          continue;
+        }
         uint32_t r[CW];
         tmem_ld16(tmem_base + acc * BN + c0 + ((uint32_t)(q * 32) << 16), r);
         if (n0 + c0 >= p.N) continue;  // warp-uniform
@@ -477,6 +532,15 @@ int launch_gemm_tc(const GemmArgs& a, cudaStream_t st) {
   p.pperiod = a.pperiod > 0 ? a.pperiod : 1; p.R = a.R; p.ldr = a.ldr; p.act = a.act;
   p.col0_bias_only = a.zero_wrow0 ? 1 : 0;
   p.has_blo = has_blo ? 1 : 0;
+  // Epilogue choice.  "direct" (TMEM fragments -> 32-byte sector stores, no shared-memory transpose) relieves the
+  // shared-memory port - the resource these GEMMs are bound by - and measures 3-6 % faster when the epilogue has no
+  // residual / periodic-bias rows to fetch (FF1, transform, logits); with them the 8-byte loads make it LSU-bound
+  // and the staged 16-byte path wins (QKVT, attention-out, FF2).  EDGL_TC_EPI=direct|staged forces one.
+  static const char epi_mode = [] {
+    const char* e = getenv("EDGL_TC_EPI");
+    return e ? e[0] : 'a';
+  }();
+  p.epi_direct = epi_mode == 'd' ? 1 : epi_mode == 's' ? 0 : (a.R == nullptr && a.pbias == nullptr) ? 1 : 0;
   p.ntn = cdiv(a.N, bn);
   const long long ntm = cdiv(a.M, BM);
   EDGL_REQUIRE(ntm * p.ntn < (1ll << 31), "gemm_tc: too many tiles");

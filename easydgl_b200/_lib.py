@@ -62,6 +62,7 @@ _SIGS = {
     "edgl_layernorm": (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
     "edgl_dense": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P]),
     "edgl_dense_nk": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P]),
+    "edgl_dense_nk_f16": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P]),
     "edgl_topk": (_I, [_P, _I, _I, _P, _I, _I, _P, _P, _P]),
 }
 EXPORTS = tuple(_SIGS)

@@ -31,6 +31,9 @@ int set_error(int code, const char* fmt, ...) {
   return code;
 }
 
+// activation-maximum slots (edgl_handle::amax)
+enum { AMAX_XA = 0, AMAX_ATT = 1, AMAX_LN1 = 2, AMAX_FF1 = 3, AMAX_LN2 = 4, AMAX_Y = 5, AMAX_COUNT = 16 };
+
 struct Tensor {
   const void* p = nullptr;
   long long numel = 0;
@@ -69,6 +72,13 @@ struct edgl_handle {
   float* pbias0 = nullptr;     // EasyDGL block 0: [L,4d] = pos_embs @ W[d:2d] + b
   std::vector<float*> wkvt, bkvt;  // CTSMA: packed [Cin,3d], [3d]
   std::vector<unsigned char*> mlp_pack;  // per block: intensity-MLP constants for attn_f16.cu (null if not covered)
+  // scaled 3xFP16 dense layers (gemm_f16.cu): fp16 hi/lo/scale copies of the K-major kernels, keyed like btT / mtT,
+  // and the running activation maxima the producers publish (zeroed at the start of every encode)
+  bool f16_gemm = false;
+  int f16_mask = 1;  // which dense layers take it: bit 0 QKVT, 1 attention-out, 2 FF1, 3 FF2, 4 transform, 5 logits
+  std::vector<std::map<std::string, unsigned char*>> bt16;
+  std::map<std::string, unsigned char*> mt16;  // "tr_w", "wfold0", "table"
+  unsigned int* amax = nullptr;                // [16]: AMAX_* slots
   // K-major ([N,K]) copies of every dense kernel for the tensor-core GEMM (made in edgl_commit)
   float* wfold0T = nullptr;                               // [4d, Ka]
   std::vector<std::map<std::string, float*>> btT;         // per block: name -> [N,K]
@@ -193,8 +203,10 @@ int dense(const float* A, int lda, const float* W, int ldw, const float* bias, f
 
 // dense layer with a K-major ([N,K]) kernel -> tensor-core path
 int dense_nk(const float* A, int lda, const float* Wt, int K, const float* bias, float* C, int ldc, long long M, int N,
-             int act, const float* R, int ldr, cudaStream_t st, bool has_lo = true) {
+             int act, const float* R, int ldr, cudaStream_t st, bool has_lo = true, const void* w16 = nullptr,
+             const unsigned int* a_amax = nullptr, unsigned int* c_amax = nullptr) {
   GemmArgs g;
+  g.W16 = w16; g.a_amax = w16 ? a_amax : nullptr; g.c_amax = c_amax;
   g.A = A; g.lda = lda; g.W = Wt; g.ldw = K; g.w_is_nk = true; g.C = C; g.ldc = ldc;
   if (has_lo) g.Wlo = Wt + (size_t)N * K;  // every K-major copy made by edgl_commit is followed by its tf32 lo part
   g.M = (int)M; g.N = N; g.K = K; g.bias = bias; g.act = act; g.R = R; g.ldr = ldr;
@@ -236,6 +248,15 @@ int encode_easydgl(edgl_handle* h, const int64_t* ids, const float* ts, int B, f
   const long long rows = (long long)B * L;
   EmbedArgs e = embed_args(h, ids, ts, B);
   e.Xa = h->xa; e.ldxa = h->Ka; e.spans = h->spans; e.marks = h->marks; e.kmask = h->kmask;
+  const bool f16 = h->f16_gemm;
+  unsigned int* const am = h->amax;
+  auto w16 = [&](int blk, const char* name, int bit) -> const void* {
+    return (f16 && ((h->f16_mask >> bit) & 1)) ? h->bt16[blk].at(name) : nullptr;
+  };
+  if (f16) {
+    EDGL_CUDA(cudaMemsetAsync(am, 0, AMAX_COUNT * sizeof(unsigned int), st));
+    e.xa_amax = am + AMAX_XA;
+  }
   mark(h, ST_EMBED, st);
   EDGL_TRY(launch_embed(e, st));
   const float* cur = h->xa;
@@ -249,33 +270,40 @@ int encode_easydgl(edgl_handle* h, const int64_t* ids, const float* ts, int B, f
       g.A = h->xa; g.lda = h->Ka; g.W = h->wfold0T; g.ldw = h->Ka; g.w_is_nk = true; g.C = h->qkvt; g.ldc = 4 * d;
       g.Wlo = h->wfold0T + (size_t)h->Ka * 4 * d;
       g.M = (int)rows; g.N = 4 * d; g.K = h->Ka; g.pbias = h->pbias0; g.pperiod = L;
+      if (f16 && (h->f16_mask & 1)) { g.W16 = h->mt16.at("wfold0"); g.a_amax = am + AMAX_XA; }
       EDGL_TRY(launch_gemm(g, st));
     } else {
       EDGL_TRY(dense_nk(cur, ldcur, h->btT[i].at("qkvt_w"), d, F(w, "qkvt_b"), h->qkvt, 4 * d, rows, 4 * d, ACT_NONE,
-                        nullptr, 0, st));
+                        nullptr, 0, st, true, w16(i, "qkvt_w", 0), am + AMAX_LN2));
     }
     AttnArgs a = attn_args(h, w, h->qkvt, h->kmask, h->spans, h->marks, cur, ldcur, h->p0, nullptr, B, false, true);
+    if (f16) a.out_amax = am + AMAX_ATT;
     mark(h, ST_ATTENTION, st);
     EDGL_TRY(launch_attention(a, st));                                                   // temporal.py:412-447
     mark(h, ST_AO_GEMM, st);
-    EDGL_TRY(dense_nk(h->p0, d, h->btT[i].at("ao_w"), d, F(w, "ao_b"), h->p1, d, rows, d, ACT_NONE, cur, ldcur, st));  // :113,116
+    EDGL_TRY(dense_nk(h->p0, d, h->btT[i].at("ao_w"), d, F(w, "ao_b"), h->p1, d, rows, d, ACT_NONE, cur, ldcur, st, true,
+                      w16(i, "ao_w", 1), am + AMAX_ATT));                                   // :113,116
     mark(h, ST_LN_ATT, st);
-    EDGL_TRY(launch_layernorm(h->p1, F(w, "ao_ln_g"), F(w, "ao_ln_b"), B, L, d, h->p0, false, st));            // :116
+    EDGL_TRY(launch_layernorm(h->p1, F(w, "ao_ln_g"), F(w, "ao_ln_b"), B, L, d, h->p0, false, st,
+                              f16 ? am + AMAX_LN1 : nullptr));                           // :116
     mark(h, ST_FF1_GEMM, st);
     EDGL_TRY(dense_nk(h->p0, d, h->btT[i].at("ff1_w"), d, F(w, "ff1_b"), h->p2, 2 * d, rows, 2 * d, ACT_GELU, nullptr,
-                      0, st));                                                           // :120-121
+                      0, st, true, w16(i, "ff1_w", 2), am + AMAX_LN1, f16 ? am + AMAX_FF1 : nullptr));  // :120-121
     mark(h, ST_FF2_GEMM, st);
     EDGL_TRY(dense_nk(h->p2, 2 * d, h->btT[i].at("ff2_w"), 2 * d, F(w, "ff2_b"), h->p1, d, rows, d, ACT_NONE, h->p0, d,
-                      st));                                                              // :125,128
+                      st, true, w16(i, "ff2_w", 3), am + AMAX_FF1));                        // :125,128
     mark(h, ST_LN_FF, st);
-    EDGL_TRY(launch_layernorm(h->p1, F(w, "ff_ln_g"), F(w, "ff_ln_b"), B, L, d, h->p2, false, st));            // :128
+    EDGL_TRY(launch_layernorm(h->p1, F(w, "ff_ln_g"), F(w, "ff_ln_b"), B, L, d, h->p2, false, st,
+                              f16 ? am + AMAX_LN2 : nullptr));                           // :128
     cur = h->p2;
     ldcur = d;
   }
   mark(h, ST_TR_GEMM, st);
-  EDGL_TRY(dense_nk(cur, ldcur, h->mtT.at("tr_w"), d, F(h->mt, "tr_b"), h->p0, d, rows, d, ACT_GELU, nullptr, 0, st));  // :138
+  EDGL_TRY(dense_nk(cur, ldcur, h->mtT.at("tr_w"), d, F(h->mt, "tr_b"), h->p0, d, rows, d, ACT_GELU, nullptr, 0, st, true,
+                    (f16 && (h->f16_mask & 16)) ? h->mt16.at("tr_w") : nullptr, am + AMAX_LN2));  // :138
   mark(h, ST_LN_OUT, st);
-  EDGL_TRY(launch_layernorm(h->p0, F(h->mt, "tr_ln_g"), F(h->mt, "tr_ln_b"), B, L, d, y, true, st));  // :139,146
+  EDGL_TRY(launch_layernorm(h->p0, F(h->mt, "tr_ln_g"), F(h->mt, "tr_ln_b"), B, L, d, y, true, st,
+                            (f16 && y == h->y) ? am + AMAX_Y : nullptr));                 // :139,146
   mark(h, ST_END, st);
   return 0;
 }
@@ -328,6 +356,10 @@ int logits_rows(edgl_handle* h, const float* y, int ldy, long long rc, float* ou
   g.A = y; g.lda = ldy;
   g.W = F(h->mt, "item_embs") + h->c0 * h->d; g.ldw = h->d; g.w_is_nk = true;
   g.Wlo = h->table_lo;
+  if (h->f16_gemm && (h->f16_mask & 32) && y == h->y && h->mt16.count("table")) {  // the local encoder's y: its maximum is in AMAX_Y
+    g.W16 = h->mt16.at("table");
+    g.a_amax = h->amax + AMAX_Y;
+  }
   g.zero_wrow0 = (h->c0 == 0);  // zero_pad=True: row 0 of the tied table is zeros (coding.py:56-57)
   g.C = out; g.ldc = ldo; g.M = (int)rc; g.N = (int)(h->c1 - h->c0); g.K = h->d;
   g.bias = h->bias_full + h->c0;
@@ -409,6 +441,7 @@ int edgl_create(const edgl_config* cfg, edgl_handle** out) {
   if (h->c0 > h->c1) h->c0 = h->c1;
   h->bt.resize(cfg->num_blocks);
   h->btT.resize(cfg->num_blocks);
+  h->bt16.resize(cfg->num_blocks);
   h->wkvt.assign(cfg->num_blocks, nullptr);
   h->bkvt.assign(cfg->num_blocks, nullptr);
   const long long rows = (long long)cfg->max_batch * h->L;
@@ -440,6 +473,20 @@ int edgl_create(const edgl_config* cfg, edgl_handle** out) {
   EDGL_ALLOC(h->marks, rows * h->E);
   EDGL_ALLOC(h->kmask, rows);
   EDGL_ALLOC(h->y, (long long)cfg->max_batch * d);
+  EDGL_ALLOC(h->amax, AMAX_COUNT);
+  {
+    // The scaled 3xFP16 dense layers (gemm_f16.cu) need every activation's running maximum from its producer, and
+    // the attention producer that publishes one is attn_f16.cu: EasyDGL with dh = 16, E = 16, L <= 208 and the default
+    // attention kernel.  By default only the block-0 QKVT layer takes it (f16_mask bit 0): it is the one dense layer
+    // bound by the shared-memory port (0.40 -> 0.35 ms at C2); attention-out / FF2 already run at 60-72 % of the HBM
+    // copy rate and FF1 / transform are bound by the erf of their GELU epilogue, so fp16 operands change nothing
+    // there (measured).  EDGL_F16_MASK=63 puts all six on it (parity-tested); EDGL_GEMM=tf32 none.
+    const char* ge = getenv("EDGL_GEMM");
+    const char* ae = getenv("EDGL_ATTN");
+    h->f16_gemm = easy && attention_f16_pack_bytes(h->dh, h->E) != 0 && h->L <= 208 && (!ae || ae[0] == 'f' || ae[0] == 'd') &&
+                  !(ge && (ge[0] == 't' || ge[0] == 's'));
+    if (const char* me = getenv("EDGL_F16_MASK")) h->f16_mask = atoi(me);
+  }
   {
     const long long Ns = h->c1 - h->c0 > 0 ? h->c1 - h->c0 : 1;
     const long long max_bt = (long long)cfg->max_batch * cfg->shard_world;
@@ -637,6 +684,25 @@ int edgl_commit(edgl_handle* h, void* stream) {
       EDGL_TRY(launch_transpose(h->wfold0, h->Ka, 4 * d, h->wfold0T, st));
       EDGL_TRY(launch_tf32_lo(h->wfold0T, (long long)h->Ka * 4 * d, h->wfold0T + (size_t)h->Ka * 4 * d, st));
     }
+  }
+  // fp16 hi / lo / scale copies of the same K-major kernels for the scaled 3xFP16 dense layers (gemm_f16.cu)
+  if (h->f16_gemm) {
+    auto split16 = [&](std::map<std::string, unsigned char*>& dst, const std::string& key, const float* wt,
+                       long long n) -> int {
+      unsigned char*& buf = dst[key];
+      if (!buf) EDGL_TRY(dev_alloc(h, &buf, w16_bytes(n)));
+      return launch_w_split_f16(wt, n, buf, st);
+    };
+    for (int i = 0; i < h->cfg.num_blocks; ++i) {
+      if (i > 0) EDGL_TRY(split16(h->bt16[i], "qkvt_w", h->btT[i].at("qkvt_w"), (long long)d * 4 * d));
+      EDGL_TRY(split16(h->bt16[i], "ao_w", h->btT[i].at("ao_w"), (long long)d * d));
+      EDGL_TRY(split16(h->bt16[i], "ff1_w", h->btT[i].at("ff1_w"), (long long)2 * d * d));
+      EDGL_TRY(split16(h->bt16[i], "ff2_w", h->btT[i].at("ff2_w"), (long long)2 * d * d));
+    }
+    EDGL_TRY(split16(h->mt16, "tr_w", h->mtT.at("tr_w"), (long long)d * d));
+    EDGL_TRY(split16(h->mt16, "wfold0", h->wfold0T, (long long)h->Ka * 4 * d));
+    const long long nt = (h->c1 - h->c0) * (long long)d;
+    if (nt * 4 <= (2ll << 30)) EDGL_TRY(split16(h->mt16, "table", F(h->mt, "item_embs") + h->c0 * d, nt));
   }
   int flag = 0;
   EDGL_CUDA(cudaMemcpyAsync(&flag, h->flag, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -880,6 +946,34 @@ int edgl_dense_nk(const float* x, const float* wt, const float* b, int M, int K,
   if (!x || !wt || !out) return set_error(EDGL_EINVAL, "null argument");
   EDGL_REQUIRE(act >= 0 && act <= 2, "dense: unknown activation %d", act);
   return dense_nk(x, K, wt, K, b, out, N, M, N, act, nullptr, 0, (cudaStream_t)stream, false);
+}
+
+int edgl_dense_nk_f16(const float* x, const float* wt, const float* b, int M, int K, int N, int act, float* out,
+                      void* stream) {
+  if (!x || !wt || !out) return set_error(EDGL_EINVAL, "null argument");
+  EDGL_REQUIRE(act >= 0 && act <= 2, "dense: unknown activation %d", act);
+  EDGL_REQUIRE(M >= 1 && N >= 1 && K >= 8 && K % 8 == 0, "dense_nk_f16: needs M, N >= 1 and K a multiple of 8");
+  cudaStream_t st = (cudaStream_t)stream;
+  // what edgl_commit (weight copies) and the producing kernel (activation maximum) do inside the pipeline
+  unsigned char* buf = nullptr;
+  const size_t wb = w16_bytes((long long)N * K);
+  EDGL_CUDA(cudaMalloc(&buf, wb + 16));
+  unsigned int* slot = reinterpret_cast<unsigned int*>(buf + wb);
+  int rc = 0;
+  if (cudaMemsetAsync(slot, 0, 16, st) != cudaSuccess) rc = set_error(EDGL_ECUDA, "cudaMemsetAsync failed");
+  if (!rc) rc = launch_w_split_f16(wt, (long long)N * K, buf, st);
+  if (!rc) rc = launch_absmax(x, (long long)M * K, slot, st);
+  if (!rc) {
+    GemmArgs g;
+    g.A = x; g.lda = K; g.W = wt; g.ldw = K; g.w_is_nk = true; g.C = out; g.ldc = N;
+    g.M = M; g.N = N; g.K = K; g.bias = b; g.act = act;
+    g.W16 = buf; g.a_amax = slot;
+    if (!gemm_f16_supported(g)) rc = set_error(EDGL_EINVAL, "dense_nk_f16: operands must be 16-byte aligned");
+    else rc = launch_gemm_f16(g, st);
+  }
+  cudaStreamSynchronize(st);
+  cudaFree(buf);
+  return rc;
 }
 
 int edgl_topk(float* logits, int B, int N, const int64_t* seen_ids, int seen_len, int K, int32_t* idx, float* val,

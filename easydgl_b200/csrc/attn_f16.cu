@@ -609,20 +609,24 @@ __global__ void __maxnreg__(MAXREG) attention_f16_kernel(AttnArgs a, int hpc) {
       const float fa = isv * isga, fb = isv * isgb;
       const float fa2 = k2m14 * isla, fb2 = k2m14 * islb;
       // ---- residual + store (temporal.py:385,447)
+      float omax = 0.f;
 #pragma unroll
       for (int n = 0; n < ND; ++n) {
         const int col = hh * DH + n * 8 + 2 * t;
         if (qa < L) {
           float2 o = make_float2(O[n][0] * fa * fa2, O[n][1] * fa * fa2);
           o.x += res_a[n].x; o.y += res_a[n].y;
+          omax = fmaxf(omax, fmaxf(fabsf(o.x), fabsf(o.y)));
           *reinterpret_cast<float2*>(a.O + (row0 + qa) * a.ldo + col) = o;
         }
         if (qb < L) {
           float2 o = make_float2(O[n][2] * fb * fb2, O[n][3] * fb * fb2);
           o.x += res_b[n].x; o.y += res_b[n].y;
+          omax = fmaxf(omax, fmaxf(fabsf(o.x), fabsf(o.y)));
           *reinterpret_cast<float2*>(a.O + (row0 + qb) * a.ldo + col) = o;
         }
       }
+      if (a.out_amax) amax_publish(a.out_amax, omax, lane);  // consumed by the scaled 3xFP16 attention-out GEMM
     }
   }
 }

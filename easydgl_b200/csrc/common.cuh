@@ -46,6 +46,17 @@ inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+#ifdef __CUDACC__
+// Running maximum of |x| over a tensor, kept as the bit pattern of a non-negative float in a device word (zeroed at
+// the start of a forward).  Producers call it once per warp with the warp's maximum; the racy read skips the atomic
+// once the slot is already at least as large (same-address atomics would otherwise serialise the whole grid).
+// Consumer: the scaled 3xFP16 GEMM (gemm_f16.cu) derives its activation scale from it.
+__device__ __forceinline__ void amax_publish(unsigned int* slot, float warp_local_max, int lane) {
+  const unsigned int bits = __reduce_max_sync(0xffffffffu, __float_as_uint(fabsf(warp_local_max)));
+  if (lane == 0 && bits > *reinterpret_cast<volatile unsigned int*>(slot)) atomicMax(slot, bits);
+}
+#endif
+
 // ------------------------------------------------------------------ kernel launchers (one per .cu)
 enum Act { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2 };
 
@@ -56,6 +67,11 @@ struct GemmArgs {
   const float* A = nullptr; int lda = 0;
   const float* W = nullptr; int ldw = 0; bool w_is_nk = false;
   const float* Wlo = nullptr;  // optional, w_is_nk only: W - tf32(W) in the layout of W (constant weights, made at commit)
+  // scaled 3xFP16 path (gemm_f16.cu), all three needed: the weight's fp16 hi/lo/scale buffer (launch_w_split_f16),
+  // the running max|A| published by A's producer, and optionally where to publish max|C| for the next layer
+  const void* W16 = nullptr;
+  const unsigned int* a_amax = nullptr;
+  unsigned int* c_amax = nullptr;
   float* C = nullptr; int ldc = 0;
   int M = 0, N = 0, K = 0;
   const float* bias = nullptr;                 // [N] or null
@@ -68,7 +84,12 @@ int launch_gemm(const GemmArgs& a, cudaStream_t st);
 bool gemm_tc_supported(const GemmArgs& a);
 int launch_gemm_tc(const GemmArgs& a, cudaStream_t st);
 int launch_transpose(const float* in, int rows, int cols, float* out, cudaStream_t st);
-int launch_tf32_lo(const float* in, long long n, float* out, cudaStream_t st);  // out = in - (in with 13 low mantissa bits cleared)
+int launch_tf32_lo(const float* in, long long n, float* out, cudaStream_t st);
+bool gemm_f16_supported(const GemmArgs& a);
+int launch_gemm_f16(const GemmArgs& a, cudaStream_t st);
+size_t w16_bytes(long long n);  // buffer size for the fp16 hi / lo / scale copies of an n-element weight
+int launch_w_split_f16(const float* w, long long n, void* buf, cudaStream_t st);
+int launch_absmax(const float* x, long long n, unsigned int* slot, cudaStream_t st);  // out = in - (in with 13 low mantissa bits cleared)
 
 struct EmbedArgs {
   int model;  // 0 EasyDGL, 1 CTSMA
@@ -82,6 +103,7 @@ struct EmbedArgs {
   // outputs (any may be null)
   float* X0; int ldx0;                         // full concat [B*L, 3d | 2d]
   float* Xa; int ldxa;                         // fused input: [x+tcode | mark-count histogram] (EasyDGL), width d+E
+  unsigned int* xa_amax;                       // optional: running max |Xa| (amax_publish), or null
   float* spans;                                // [B*L]
   uint8_t* marks;                              // [B*L,E]
   uint8_t* kmask;                              // [B*L]
@@ -109,6 +131,7 @@ struct AttnArgs {
   int B, L, d, h, E;
   bool causal, diag_one;
   const void* mlp_pack = nullptr;  // attn_f16.cu: constants of the intensity MLP packed at commit, or null
+  unsigned int* out_amax = nullptr;  // attn_f16.cu only: running max |O| (amax_publish), or null
 };
 int launch_attention(const AttnArgs& a, cudaStream_t st);
 // scaled 3xFP16 mma.sync kernel (attn_f16.cu): 0 = launched, 1 = shape not covered, <0 = error
@@ -123,7 +146,7 @@ int launch_intensity(const float* H, const float* spans, const uint8_t* marks, c
 
 // LayerNorm over (L,C) jointly per sample. last_only: write only row L-1 to out [B,C].
 int launch_layernorm(const float* x, const float* gamma, const float* beta, int B, int L, int C, float* out,
-                     bool last_only, cudaStream_t st);
+                     bool last_only, cudaStream_t st, unsigned int* out_amax = nullptr);
 
 int launch_mask_seen(float* logits, int ld, int B, const int64_t* ids, int seen_len, long long seen_stride,
                      long long col0, long long col1, cudaStream_t st);

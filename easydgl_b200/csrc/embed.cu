@@ -46,6 +46,7 @@ __global__ void __launch_bounds__(128) embed_kernel(EmbedArgs a, float sqrt_d) {
     for (int e = lane; e < E; e += 32) a.marks[row * E + e] = mid_ok ? mrow[e] : (uint8_t)0;
 
   const float* irow = a.item_table + (id_ok ? id : 0) * (long long)d;
+  float xmax = 0.f;  // max |Xa| of this row (the histogram counts are at most E)
   for (int j = lane; j < half; j += 32) {
     float2 it = id_ok ? ld2(irow + 2 * j) : make_float2(0.f, 0.f);
     float x0 = __fmul_rn(it.x, sqrt_d), x1 = __fmul_rn(it.y, sqrt_d);  // coding.py:61-63
@@ -57,6 +58,7 @@ __global__ void __launch_bounds__(128) embed_kernel(EmbedArgs a, float sqrt_d) {
     }
     if (a.X0) st2(a.X0 + row * a.ldx0 + 2 * j, x0, x1);
     if (a.Xa) st2(a.Xa + row * a.ldxa + 2 * j, x0, x1);
+    xmax = fmaxf(xmax, fmaxf(fabsf(x0), fabsf(x1)));
     if (a.X0) {
       float2 p = ld2(a.pos_table + (long long)l * d + 2 * j);  // coding.py:76-79
       st2(a.X0 + row * a.ldx0 + d + 2 * j, p.x, p.y);
@@ -75,6 +77,7 @@ __global__ void __launch_bounds__(128) embed_kernel(EmbedArgs a, float sqrt_d) {
       }
     }
   }
+  if (a.Xa && a.xa_amax) amax_publish(a.xa_amax, fmaxf(xmax, a.model == 0 ? (float)E : 0.f), lane);
   if (a.Xa && a.model == 0) {
     // histogram of mark values: cnt[v] = #{e : marks[e] == v}; the mark code is cnt @ mark_embs_zp,
     // so the block-0 QKVT dense sees it through a [E,4d] folded kernel (api.cu commit()).

@@ -231,6 +231,7 @@ int launch_gemm(const GemmArgs& a, cudaStream_t st) {
     const char* e = getenv("EDGL_GEMM");
     return e && e[0] == 's';
   }();
+  if (!force_simt && gemm_f16_supported(a)) return launch_gemm_f16(a, st);  // scaled 3xFP16 on kind::f16
   if (!force_simt && gemm_tc_supported(a)) return launch_gemm_tc(a, st);
   const int ntn = cdiv(a.N, BN);
   const long long ntm = cdiv(a.M, BM);

@@ -24,7 +24,8 @@ __device__ __forceinline__ float block_sum_256(float v, float* red) {
 template <bool CACHE>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, int L, int C,
-                                                        float* __restrict__ out, int last_only) {
+                                                        float* __restrict__ out, int last_only,
+                                                        unsigned int* __restrict__ out_amax) {
   extern __shared__ __align__(16) float xs[];
   __shared__ float red[8];
   const long long n = (long long)L * C;
@@ -45,12 +46,15 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   }
   const float var = block_sum_256(q, red) / (float)n;
   const float rstd = __frcp_rn(sqrtf(var + 1e-12f));
+  float omax = 0.f;  // max |out| over what this thread writes
   if (last_only) {
     const float* src = (CACHE ? xs : xp) + (long long)(L - 1) * C;
     float* op = out + (long long)blockIdx.x * C;
     for (int c = threadIdx.x; c < C; c += 256) {
       const float inv = rstd * gamma[c];
-      op[c] = src[c] * inv + (beta[c] - mean * inv);
+      const float o = src[c] * inv + (beta[c] - mean * inv);
+      op[c] = o;
+      omax = fmaxf(omax, fabsf(o));
     }
   } else {
     float* op = out + (long long)blockIdx.x * n;
@@ -67,12 +71,14 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
       inv = rstd * g.z; o.z = v.z * inv + (bt.z - mean * inv);
       inv = rstd * g.w; o.w = v.w * inv + (bt.w - mean * inv);
       reinterpret_cast<float4*>(op)[i] = o;
+      omax = fmaxf(omax, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
     }
   }
+  if (out_amax) amax_publish(out_amax, omax, threadIdx.x & 31);
 }
 
 int launch_layernorm(const float* x, const float* gamma, const float* beta, int B, int L, int C, float* out,
-                     bool last_only, cudaStream_t st) {
+                     bool last_only, cudaStream_t st, unsigned int* out_amax) {
   EDGL_REQUIRE(C % 4 == 0, "layernorm: channel count must be a multiple of 4 (got %d)", C);
   EDGL_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
                    (reinterpret_cast<uintptr_t>(gamma) & 15) == 0 && (reinterpret_cast<uintptr_t>(beta) & 15) == 0,
@@ -82,9 +88,9 @@ int launch_layernorm(const float* x, const float* gamma, const float* beta, int 
   if (bytes <= 200 * 1024) {
     auto kern = layernorm_kernel<true>;
     EDGL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    kern<<<B, 256, bytes, st>>>(x, gamma, beta, L, C, out, last_only ? 1 : 0);
+    kern<<<B, 256, bytes, st>>>(x, gamma, beta, L, C, out, last_only ? 1 : 0, out_amax);
   } else {
-    layernorm_kernel<false><<<B, 256, 0, st>>>(x, gamma, beta, L, C, out, last_only ? 1 : 0);
+    layernorm_kernel<false><<<B, 256, 0, st>>>(x, gamma, beta, L, C, out, last_only ? 1 : 0, out_amax);
   }
   EDGL_LAUNCH_CHECK();
   return 0;

@@ -327,8 +327,9 @@ def dense(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], act: int 
     return out
 
 
-def dense_nk(x: torch.Tensor, wt: torch.Tensor, b: Optional[torch.Tensor], act: int = 0) -> torch.Tensor:
-    """dense layer with the kernel stored K-major (wt [N,K]): the tcgen05 tensor-core GEMM."""
+def dense_nk(x: torch.Tensor, wt: torch.Tensor, b: Optional[torch.Tensor], act: int = 0, f16: bool = False) -> torch.Tensor:
+    """dense layer with the kernel stored K-major (wt [N,K]): the tcgen05 tensor-core GEMM (3xTF32, or the scaled
+    3xFP16 split with f16=True)."""
     lib = _lib.load()
     x = _req(x, torch.float32, "x")
     wt = _req(wt, torch.float32, "wt", x.device)
@@ -337,7 +338,8 @@ def dense_nk(x: torch.Tensor, wt: torch.Tensor, b: Optional[torch.Tensor], act: 
     out = torch.empty(tuple(x.shape[:-1]) + (N,), dtype=torch.float32, device=x.device)
     bb = None if b is None else _req(b, torch.float32, "b", x.device)
     with torch.cuda.device(x.device):
-        check(lib.edgl_dense_nk(x.data_ptr(), wt.data_ptr(), _ptr(bb), M, K, N, act, out.data_ptr(), _stream()))
+        fn = lib.edgl_dense_nk_f16 if f16 else lib.edgl_dense_nk
+        check(fn(x.data_ptr(), wt.data_ptr(), _ptr(bb), M, K, N, act, out.data_ptr(), _stream()))
     return out
 
 

@@ -195,6 +195,12 @@ int edgl_dense(const float* x, const float* w, const float* b, int M, int K, int
  * the tcgen05 tensor-core path (3xTF32, fp32-level accuracy). */
 int edgl_dense_nk(const float* x, const float* wt, const float* b, int M, int K, int N, int act, float* out,
                   void* stream);
+/* Same layer on the scaled 3xFP16 tensor-core path (tcgen05 kind::f16; fp32-level accuracy relative to
+ * max|x| * |w|): K must be a multiple of 8.  Inside the model pipeline the weight copies are made by edgl_commit and
+ * the activation maximum comes from the kernel that produced x; this stand-alone entry computes both first and
+ * synchronises the stream before returning (a test / tooling entry, not a hot-path one). */
+int edgl_dense_nk_f16(const float* x, const float* wt, const float* b, int M, int K, int N, int act, float* out,
+                      void* stream);
 /* Sequential.eval ranking on given logits (Base.py:156-181): logits [B,N] are modified in place
  * (seen ids -> -inf) when seen_ids != NULL. */
 int edgl_topk(float* logits, int B, int N, const int64_t* seen_ids, int seen_len, int K, int32_t* idx,

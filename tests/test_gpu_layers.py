@@ -146,6 +146,26 @@ def test_dense_tensor_core(M, K, N, act):
     assert_close(out, ref, 1e-5, "tensor-core dense act=%d" % act)
 
 
+@pytest.mark.parametrize("M,K,N,act", [(128, 32, 128, 0), (5, 32, 16, 0), (130, 64, 128, 1), (257, 144, 512, 0),
+                                       (300, 128, 256, 2), (1000, 256, 128, 1), (77, 128, 18001, 0),
+                                       (40000, 128, 128, 0), (20000, 144, 512, 1)])
+def test_dense_tensor_core_f16_split(M, K, N, act):
+    """The tcgen05 kind::f16 GEMM with the scaled 3xFP16 split (gemm_f16.cu): same bar as the 3xTF32 kernel -
+    fp32-level accuracy relative to max|ref| - with rows whose magnitudes differ by 2^12 and a K tail."""
+    from easydgl_b200 import engine
+    g = torch.Generator().manual_seed(60 + M % 7)
+    x = torch.randn(M, K, generator=g) * torch.exp2(-torch.randint(0, 13, (M, 1), generator=g).float())
+    w = torch.randn(K, N, generator=g) / math.sqrt(K)
+    b = torch.randn(N, generator=g) * 1e-3
+    out = engine.dense_nk(x.to(DEV), w.t().contiguous().to(DEV), b.to(DEV), act, f16=True).cpu()
+    ref = x.double() @ w.double() + b.double()
+    if act == 1:
+        ref = O.gelu(ref)
+    elif act == 2:
+        ref = torch.relu(ref)
+    assert_close(out, ref, 1e-5, "3xFP16 tensor-core dense act=%d" % act)
+
+
 @pytest.mark.parametrize("name", ["easy_a", "easy_b", "easy_c", "ctsma_b"])
 def test_intensity(name):
     """T.MAU.intensity (temporal.py:281-315): G [hB,L,L] and lam [hB,L,E], literal 4-D form as reference."""

@@ -229,6 +229,22 @@ def test_attention_variant_layers(mode):
     assert "VARIANT_OK" in res.stdout, res.stdout[-3000:] + res.stderr[-2000:]
 
 
+def test_f16_dense_layers_in_pipeline():
+    """The scaled 3xFP16 dense layers (gemm_f16.cu) inside the C2 pipeline, fed by the producers' published activation
+    maxima: none (mask 0), the default (QKVT), and all six - each within 1e-4 of the fp64 oracle's logits (the
+    measured errors are 1.4e-6 ... 2.1e-6, the same as the 3xTF32 layers)."""
+    import subprocess
+    import sys
+    script = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "check_f16_gemm_mask.py")
+    res = subprocess.run([sys.executable, script, "0", "1", "63"], capture_output=True, text=True, timeout=280,
+                         cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    lines = [l for l in res.stdout.splitlines() if l.startswith("mask")]
+    assert len(lines) == 3, res.stdout[-2000:] + res.stderr[-2000:]
+    for l in lines:
+        assert "finite True" in l, l
+        assert float(l.split("err")[1].split()[0]) < 1e-4, l
+
+
 def test_long_sequence_key_streaming_path():
     """L = 300 (> every register/TMEM-resident kernel's limit) and dh = 32: the key-streaming kernel."""
     _check_model("easy_b", batch=3, seqslen=299)

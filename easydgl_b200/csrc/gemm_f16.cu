@@ -137,6 +137,7 @@ __device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_
 }
 
 struct Params {
+  int gelu_fit;  // GELU epilogue: 1 = gelu_fit (default), 0 = exact erff (EDGL_GELU=erf)
   float* C; int ldc;
   int M, N, K;
   const float* bias;
@@ -151,7 +152,27 @@ struct Params {
   unsigned int* c_amax;        // optional: publish max|C| for the next layer
 };
 
-__device__ __forceinline__ float gelu_erf_f(float x) {
+// GELU(x) = x * 0.5 * (1 + erf(x / sqrt 2)) (EasyDGL.py:31-32, Q18) with a branch-free erf:
+//   erf(t) = 1 - 2^(-t * g(t)),  g = degree-7 minimax fit of -log2(erfc(t)) / t on [0, 4] (erf(t >= 4) = 1 in fp32).
+// Max |erf error| 1.0e-7, i.e. the rounding of an fp32 erff; the resulting GELU differs from the float64 one by at
+// most 1.1e-7 * |x| - the same bound as the erff-based fp32 form (fit and emulation: DESIGN.md 4).  14 instructions
+// instead of ~45: the GELU epilogues (FF1, transform) are bound by exactly these issue slots.
+__device__ __forceinline__ float gelu_fit(float x) {
+  const float t = fminf(fabsf(x) * 0.70710678118654752440f, 4.0f);
+  float p = 4.5358559873420745e-05f;
+  p = fmaf(p, t, -0.00044550723396241665f);
+  p = fmaf(p, t, 0.0014894399791955948f);
+  p = fmaf(p, t, 0.0007746326737105846f);
+  p = fmaf(p, t, -0.02825368382036686f);
+  p = fmaf(p, t, 0.14848162233829498f);
+  p = fmaf(p, t, 0.9184163808822632f);
+  p = fmaf(p, t, 1.6279085874557495f);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-t * p));
+  return fmaf(fabsf(x), fmaf(e, -0.5f, 0.5f), 0.5f * x);
+}
+
+__device__ __forceinline__ float gelu_erf_f_exact(float x) {
   return x * (0.5f * (1.0f + erff(x * 0.70710678118654752440f)));  // EasyDGL.py:31-32
 }
 
@@ -366,7 +387,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 float2 v = make_float2(__uint_as_float(r8[4 * j + 2 * h8]) * inv, __uint_as_float(r8[4 * j + 2 * h8 + 1]) * inv);
                 if (p.col0_bias_only && col == 0) v.x = 0.f;
                 v.x += add[h8][j].x; v.y += add[h8][j].y;
-                if (ACT == ACT_GELU) { v.x = gelu_erf_f(v.x); v.y = gelu_erf_f(v.y); }
+                if (ACT == ACT_GELU) { v.x = (p.gelu_fit ? gelu_fit(v.x) : gelu_erf_f_exact(v.x)); v.y = (p.gelu_fit ? gelu_fit(v.y) : gelu_erf_f_exact(v.y)); }
                 if (ACT == ACT_RELU) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); }
                 v.x += res[h8][j].x; v.y += res[h8][j].y;
                 if (row < p.M) {
@@ -411,7 +432,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             if (p.col0_bias_only && col == 0) v.x = 0.f;
             if (p.pbias) { v.x += pp[itr].x; v.y += pp[itr].y; v.z += pp[itr].z; v.w += pp[itr].w; }
             v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
-            if (ACT == ACT_GELU) { v.x = gelu_erf_f(v.x); v.y = gelu_erf_f(v.y); v.z = gelu_erf_f(v.z); v.w = gelu_erf_f(v.w); }
+            if (ACT == ACT_GELU) { v.x = (p.gelu_fit ? gelu_fit(v.x) : gelu_erf_f_exact(v.x)); v.y = (p.gelu_fit ? gelu_fit(v.y) : gelu_erf_f_exact(v.y)); v.z = (p.gelu_fit ? gelu_fit(v.z) : gelu_erf_f_exact(v.z)); v.w = (p.gelu_fit ? gelu_fit(v.w) : gelu_erf_f_exact(v.w)); }
             if (ACT == ACT_RELU) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
             if (p.R) { v.x += rr[itr].x; v.y += rr[itr].y; v.z += rr[itr].z; v.w += rr[itr].w; }
             if (row < p.M) {
@@ -433,7 +454,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
               if (p.col0_bias_only && c == 0) x = 0.f;
               if (p.pbias) x += p.pbias[(size_t)(row % p.pperiod) * p.N + c];
               if (p.bias) x += p.bias[c];
-              if (ACT == ACT_GELU) x = gelu_erf_f(x);
+              if (ACT == ACT_GELU) x = (p.gelu_fit ? gelu_fit(x) : gelu_erf_f_exact(x));
               if (ACT == ACT_RELU) x = fmaxf(x, 0.f);
               if (p.R) x += p.R[(size_t)row * p.ldr + c];
               p.C[(size_t)row * p.ldc + c] = x;
@@ -573,6 +594,8 @@ int launch_gemm_f16(const GemmArgs& a, cudaStream_t st) {
   p.C = a.C; p.ldc = a.ldc; p.M = a.M; p.N = a.N; p.K = a.K; p.bias = a.bias; p.pbias = a.pbias;
   p.pperiod = a.pperiod > 0 ? a.pperiod : 1; p.R = a.R; p.ldr = a.ldr; p.act = a.act;
   p.col0_bias_only = a.zero_wrow0 ? 1 : 0;
+  static const bool gelu_exact = [] { const char* e = getenv("EDGL_GELU"); return e && e[0] == 'e'; }();
+  p.gelu_fit = gelu_exact ? 0 : 1;
   p.a_amax = a.a_amax; p.w_inv = winv; p.c_amax = a.c_amax;
   static const char epi_mode = [] {
     const char* e = getenv("EDGL_TC_EPI");

@@ -135,6 +135,7 @@ __device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, uint32_t (&r)
 }
 
 struct Params {
+  int gelu_fit;  // GELU epilogue: 1 = gelu_fit (default), 0 = exact erff (EDGL_GELU=erf)
   float* C; int ldc;
   int M, N, K;
   const float* bias;
@@ -149,7 +150,27 @@ struct Params {
   long long* dbg;  // optional [gridDim][8] cycle counters (EDGL_TC_DEBUG), else null
 };
 
-__device__ __forceinline__ float gelu_erf_tc(float x) {
+// GELU(x) = x * 0.5 * (1 + erf(x / sqrt 2)) (EasyDGL.py:31-32, Q18) with a branch-free erf:
+//   erf(t) = 1 - 2^(-t * g(t)),  g = degree-7 minimax fit of -log2(erfc(t)) / t on [0, 4] (erf(t >= 4) = 1 in fp32).
+// Max |erf error| 1.0e-7, i.e. the rounding of an fp32 erff; the resulting GELU differs from the float64 one by at
+// most 1.1e-7 * |x| - the same bound as the erff-based fp32 form (fit and emulation: DESIGN.md 4).  14 instructions
+// instead of ~45: the GELU epilogues (FF1, transform) are bound by exactly these issue slots.
+__device__ __forceinline__ float gelu_fit(float x) {
+  const float t = fminf(fabsf(x) * 0.70710678118654752440f, 4.0f);
+  float p = 4.5358559873420745e-05f;
+  p = fmaf(p, t, -0.00044550723396241665f);
+  p = fmaf(p, t, 0.0014894399791955948f);
+  p = fmaf(p, t, 0.0007746326737105846f);
+  p = fmaf(p, t, -0.02825368382036686f);
+  p = fmaf(p, t, 0.14848162233829498f);
+  p = fmaf(p, t, 0.9184163808822632f);
+  p = fmaf(p, t, 1.6279085874557495f);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-t * p));
+  return fmaf(fabsf(x), fmaf(e, -0.5f, 0.5f), 0.5f * x);
+}
+
+__device__ __forceinline__ float gelu_erf_tc_exact(float x) {
   return x * (0.5f * (1.0f + erff(x * 0.70710678118654752440f)));  // EasyDGL.py:31-32 (x/sqrt(2) as x*(1/sqrt 2): <= 1 ulp)
 }
 
@@ -380,7 +401,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 float2 v = make_float2(__uint_as_float(r8[4 * j + 2 * h8]), __uint_as_float(r8[4 * j + 2 * h8 + 1]));
                 if (p.col0_bias_only && col == 0) v.x = 0.f;
                 v.x += add[h8][j].x; v.y += add[h8][j].y;
-                if (ACT == ACT_GELU) { v.x = gelu_erf_tc(v.x); v.y = gelu_erf_tc(v.y); }
+                if (ACT == ACT_GELU) { v.x = (p.gelu_fit ? gelu_fit(v.x) : gelu_erf_tc_exact(v.x)); v.y = (p.gelu_fit ? gelu_fit(v.y) : gelu_erf_tc_exact(v.y)); }
                 if (ACT == ACT_RELU) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); }
                 v.x += res[h8][j].x; v.y += res[h8][j].y;
                 if (row < p.M) *reinterpret_cast<float2*>(p.C + (size_t)row * p.ldc + col) = v;
@@ -422,7 +443,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             if (p.col0_bias_only && col == 0) v.x = 0.f;
             if (p.pbias) { v.x += pp[itr].x; v.y += pp[itr].y; v.z += pp[itr].z; v.w += pp[itr].w; }
             v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
-            if (ACT == ACT_GELU) { v.x = gelu_erf_tc(v.x); v.y = gelu_erf_tc(v.y); v.z = gelu_erf_tc(v.z); v.w = gelu_erf_tc(v.w); }
+            if (ACT == ACT_GELU) { v.x = (p.gelu_fit ? gelu_fit(v.x) : gelu_erf_tc_exact(v.x)); v.y = (p.gelu_fit ? gelu_fit(v.y) : gelu_erf_tc_exact(v.y)); v.z = (p.gelu_fit ? gelu_fit(v.z) : gelu_erf_tc_exact(v.z)); v.w = (p.gelu_fit ? gelu_fit(v.w) : gelu_erf_tc_exact(v.w)); }
             if (ACT == ACT_RELU) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
             if (p.R) { v.x += rr[itr].x; v.y += rr[itr].y; v.z += rr[itr].z; v.w += rr[itr].w; }
             if (row < p.M) *reinterpret_cast<float4*>(p.C + (size_t)row * p.ldc + col) = v;
@@ -441,7 +462,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
               if (p.col0_bias_only && c == 0) x = 0.f;
               if (p.pbias) x += p.pbias[(size_t)(row % p.pperiod) * p.N + c];
               if (p.bias) x += p.bias[c];
-              if (ACT == ACT_GELU) x = gelu_erf_tc(x);
+              if (ACT == ACT_GELU) x = (p.gelu_fit ? gelu_fit(x) : gelu_erf_tc_exact(x));
               if (ACT == ACT_RELU) x = fmaxf(x, 0.f);
               if (p.R) x += p.R[(size_t)row * p.ldr + c];
               p.C[(size_t)row * p.ldc + c] = x;
@@ -531,6 +552,8 @@ int launch_gemm_tc(const GemmArgs& a, cudaStream_t st) {
   p.C = a.C; p.ldc = a.ldc; p.M = a.M; p.N = a.N; p.K = a.K; p.bias = a.bias; p.pbias = a.pbias;
   p.pperiod = a.pperiod > 0 ? a.pperiod : 1; p.R = a.R; p.ldr = a.ldr; p.act = a.act;
   p.col0_bias_only = a.zero_wrow0 ? 1 : 0;
+  static const bool gelu_exact = [] { const char* e = getenv("EDGL_GELU"); return e && e[0] == 'e'; }();
+  p.gelu_fit = gelu_exact ? 0 : 1;
   p.has_blo = has_blo ? 1 : 0;
   // Epilogue choice.  "direct" (TMEM fragments -> 32-byte sector stores, no shared-memory transpose) relieves the
   // shared-memory port - the resource these GEMMs are bound by - and measures 3-6 % faster when the epilogue has no

@@ -17,6 +17,8 @@ SMALL = {
     "easy_a": dict(model="EasyDGL", num_units=32, seqslen=12, num_items=200, num_heads=4, num_blocks=2, num_events=8),
     "easy_b": dict(model="EasyDGL", num_units=64, seqslen=30, num_items=500, num_heads=2, num_blocks=1, num_events=16),
     "easy_c": dict(model="EasyDGL", num_units=64, seqslen=36, num_items=333, num_heads=4, num_blocks=1, num_events=4),
+    # dh = 16, E = 16 at a short L: the scaled 3xFP16 attention (NT = 4) and QKVT GEMM (K = 80) - the smoke() config
+    "easy_d": dict(model="EasyDGL", num_units=64, seqslen=30, num_items=500, num_heads=4, num_blocks=1, num_events=16),
     "ctsma_a": dict(model="CTSMA", num_units=32, seqslen=13, num_items=200, num_heads=4, num_blocks=2, num_events=8),
     "ctsma_b": dict(model="CTSMA", num_units=64, seqslen=30, num_items=500, num_heads=4, num_blocks=2, num_events=16),
 }

@@ -64,7 +64,7 @@ def _check_model(name, batch, mode="parity", k=100, **over):
     return eng, cfg, inp, W, logits, idx, val
 
 
-@pytest.mark.parametrize("name", ["easy_a", "easy_b", "easy_c", "ctsma_a", "ctsma_b"])
+@pytest.mark.parametrize("name", ["easy_a", "easy_b", "easy_c", "easy_d", "ctsma_a", "ctsma_b"])
 def test_forward_small_parity_weights(name):
     _check_model(name, batch=8)
 

@@ -379,10 +379,9 @@ int launch_attention(const AttnArgs& a, cudaStream_t st) {
     return e ? e[0] : 'd';
   }();
   const bool force_simt = mode == 's';
-  // EDGL_ATTN=tc: the tcgen05 / TMEM kernel (attn_tc.cu; dh = 16, E = 16, L <= 128).  It passes the same
-  // parity tests but its phases are serialised per (sequence, head) item - one item fills the 512 TMEM
-  // columns - so it is slower (3.4 ms vs 2.1 ms at C2) than the register-resident mma.sync kernel, which
-  // stays the default until the TMEM budget allows two items in flight.
+  // EDGL_ATTN=tc: the tcgen05 / TMEM kernel (attn_tc.cu; dh = 16, E = 16, L <= 128).  It passes the same parity
+  // tests but, with one thread per query row, is latency-bound (2.4 ms at C2 against 1.35 ms for the default
+  // attn_f16.cu); docs/attn_tc2_design.md describes the column-parallel successor.
   if (mode == 't') {
     const int r = launch_attention_tc(a, st);
     if (r <= 0) return r;

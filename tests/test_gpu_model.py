@@ -229,6 +229,31 @@ def test_attention_variant_layers(mode):
     assert "VARIANT_OK" in res.stdout, res.stdout[-3000:] + res.stderr[-2000:]
 
 
+@pytest.mark.parametrize("env", [{"EDGL_TC_EPI": "staged"}, {"EDGL_GELU": "erf"}, {"EDGL_TC_NOBLO": "1"},
+                                 {"EDGL_GEMM": "tf32"}],
+                         ids=lambda e: "-".join("%s=%s" % kv for kv in e.items()))
+def test_dense_layer_variants_agree(env):
+    """The selectable implementations of the tensor-core dense layers (staged epilogue everywhere, erff GELU, in-kernel W
+    split, no fp16 layer) meet the same bar as the defaults.  Subprocess: the switches are read once per process."""
+    import subprocess
+    import sys
+    code = (
+        "import sys, torch; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "from helpers import O, case, assert_close\n"
+        "from easydgl_b200.engine import Engine\n"
+        "for name in ('easy_b', 'easy_d', 'ctsma_b', 'C2'):\n"
+        "    cfg, inp, W = case(name, batch=8)\n"
+        "    eng = Engine(cfg, W, max_batch=8, device='cuda:0')\n"
+        "    lg = eng.forward_logits(inp['seqs_i'].cuda(), inp['seqs_t'].cuda()).cpu()\n"
+        "    ref = O.forward(inp['seqs_i'], inp['seqs_t'], W, cfg, dtype=torch.float64)\n"
+        "    assert_close(lg[:, 1:], ref[:, 1:], 1e-3, name)\n"
+        "print('VARIANT_OK')\n" % (os.path.dirname(os.path.abspath(__file__)),
+                                   os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+    res = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True,
+                         timeout=280)
+    assert "VARIANT_OK" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
+
+
 def test_f16_dense_layers_in_pipeline():
     """The scaled 3xFP16 dense layers (gemm_f16.cu) inside the C2 pipeline, fed by the producers' published activation
     maxima: none (mask 0), the default (QKVT), and all six - each within 1e-4 of the fp64 oracle's logits (the

@@ -18,58 +18,20 @@
 #include <cuda.h>
 #include <stdlib.h>
 
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace edgl {
 
 namespace tc {
 
+using namespace tcc;
+
 constexpr int BM = 128;      // UMMA M
-constexpr int BK = 32;       // floats per k-block = one 128-byte swizzle row
+// BK (tc_common.cuh) = 32 floats per k-block = one 128-byte swizzle row
 constexpr int UK = 8;        // UMMA K for tf32 (32 bytes)
 constexpr int NTHREADS = 512;
 constexpr int CW = 16;       // epilogue sub-chunk width (columns per tcgen05.ld)
 constexpr int CP = CW + 4;   // padded pitch of the epilogue staging tile
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "DONE:\n\t"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-          smem_u32(dst)),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
-  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(map)),
-               "r"(c0), "r"(c1)
-               : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // K-major, 128B-swizzled shared-memory operand descriptor (rows of 128 B, 8-row groups 1024 B apart)
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
@@ -96,10 +58,6 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -109,27 +67,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
         "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// 16 TMEM lanes x 16 columns as an MMA-accumulator-style fragment: thread (g = lane/4, t = lane%4) gets, for each
-// 8-column group j, r[4j], r[4j+1] = row g, columns 8j + 2t, 2t+1 and r[4j+2], r[4j+3] = row g + 8, same columns.
-// A quad then owns 32 contiguous bytes of a row: rows can be stored straight from registers, sector by sector.
-__device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, uint32_t (&r)[8]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
@@ -489,38 +426,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   }
 }
 
-// ---------------------------------------------------------------------------------------------- host
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode() {
-  static EncodeTiledFn fn = [] {
-    void* f = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
-        q != cudaDriverEntryPointSuccess)
-      f = nullptr;
-    return reinterpret_cast<EncodeTiledFn>(f);
-  }();
-  return fn;
-}
-
-// 2-D fp32 tensor [rows][cols] with row pitch ld floats; box = [box_rows][32 floats], 128B swizzle
-static int make_map(CUtensorMap* m, const float* ptr, long long rows, long long cols, long long ld, int box_rows) {
-  EncodeTiledFn enc = get_encode();
-  if (!enc) return set_error(-3, "cuTensorMapEncodeTiled is not available from the driver");
-  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return set_error(-3, "cuTensorMapEncodeTiled failed (%d)", (int)r);
-  return 0;
-}
-
 }  // namespace tc
 
 // Can this GEMM go through the tensor-core kernel?  (W must be [N,K] K-major.)
@@ -543,11 +448,11 @@ int launch_gemm_tc(const GemmArgs& a, cudaStream_t st) {
   if (a.M == 0) return 0;
   const int bn = a.N > 128 ? 256 : 128;
   CUtensorMap mapA, mapB, mapBlo;
-  EDGL_TRY(make_map(&mapA, a.A, a.M, a.K, a.lda, BM));
-  EDGL_TRY(make_map(&mapB, a.W, a.N, a.K, a.ldw, bn));
+  EDGL_TRY(make_map(&mapA, a.A, false, a.M, a.K, a.lda, BM));
+  EDGL_TRY(make_map(&mapB, a.W, false, a.N, a.K, a.ldw, bn));
   static const bool no_blo = getenv("EDGL_TC_NOBLO") != nullptr;  // A/B switch for measurements
   const bool has_blo = a.Wlo != nullptr && !no_blo && (reinterpret_cast<uintptr_t>(a.Wlo) & 15) == 0;
-  EDGL_TRY(make_map(&mapBlo, has_blo ? a.Wlo : a.W, a.N, a.K, a.ldw, bn));
+  EDGL_TRY(make_map(&mapBlo, has_blo ? a.Wlo : a.W, false, a.N, a.K, a.ldw, bn));
   Params p;
   p.C = a.C; p.ldc = a.ldc; p.M = a.M; p.N = a.N; p.K = a.K; p.bias = a.bias; p.pbias = a.pbias;
   p.pperiod = a.pperiod > 0 ? a.pperiod : 1; p.R = a.R; p.ldr = a.ldr; p.act = a.act;

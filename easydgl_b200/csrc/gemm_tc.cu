@@ -26,12 +26,9 @@ namespace tc {
 
 using namespace tcc;
 
-constexpr int BM = 128;      // UMMA M
 // BK (tc_common.cuh) = 32 floats per k-block = one 128-byte swizzle row
 constexpr int UK = 8;        // UMMA K for tf32 (32 bytes)
 constexpr int NTHREADS = 512;
-constexpr int CW = 16;       // epilogue sub-chunk width (columns per tcgen05.ld)
-constexpr int CP = CW + 4;   // padded pitch of the epilogue staging tile
 
 // K-major, 128B-swizzled shared-memory operand descriptor (rows of 128 B, 8-row groups 1024 B apart)
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
@@ -86,30 +83,6 @@ struct Params {
                 // it in like W and the splitter warps only split the activations
   long long* dbg;  // optional [gridDim][8] cycle counters (EDGL_TC_DEBUG), else null
 };
-
-// GELU(x) = x * 0.5 * (1 + erf(x / sqrt 2)) (EasyDGL.py:31-32, Q18) with a branch-free erf:
-//   erf(t) = 1 - 2^(-t * g(t)),  g = degree-7 minimax fit of -log2(erfc(t)) / t on [0, 4] (erf(t >= 4) = 1 in fp32).
-// Max |erf error| 1.0e-7, i.e. the rounding of an fp32 erff; the resulting GELU differs from the float64 one by at
-// most 1.1e-7 * |x| - the same bound as the erff-based fp32 form (fit and emulation: DESIGN.md 4).  14 instructions
-// instead of ~45: the GELU epilogues (FF1, transform) are bound by exactly these issue slots.
-__device__ __forceinline__ float gelu_fit(float x) {
-  const float t = fminf(fabsf(x) * 0.70710678118654752440f, 4.0f);
-  float p = 4.5358559873420745e-05f;
-  p = fmaf(p, t, -0.00044550723396241665f);
-  p = fmaf(p, t, 0.0014894399791955948f);
-  p = fmaf(p, t, 0.0007746326737105846f);
-  p = fmaf(p, t, -0.02825368382036686f);
-  p = fmaf(p, t, 0.14848162233829498f);
-  p = fmaf(p, t, 0.9184163808822632f);
-  p = fmaf(p, t, 1.6279085874557495f);
-  float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-t * p));
-  return fmaf(fabsf(x), fmaf(e, -0.5f, 0.5f), 0.5f * x);
-}
-
-__device__ __forceinline__ float gelu_erf_tc_exact(float x) {
-  return x * (0.5f * (1.0f + erff(x * 0.70710678118654752440f)));  // EasyDGL.py:31-32 (x/sqrt(2) as x*(1/sqrt 2): <= 1 ulp)
-}
 
 template <int BN>
 struct Smem {
@@ -278,8 +251,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     constexpr int LPR = CW / 4;        // lanes per row (4)
     constexpr int RPI = 32 / LPR;      // rows per warp instruction (8)
     constexpr int NIT = 32 / RPI;      // iterations per sub-chunk (4)
-    const int cl = (lane % LPR) * 4;   // this lane's 4 columns inside a sub-chunk
-    const int rsub = lane / LPR;       // this lane's row inside a group of RPI
+    const int rsub = lane / LPR;       // this lane's row inside a group of RPI (staged path)
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tcount) {
       const int acc = tcount & 1;
@@ -306,108 +278,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       const long long t1 = clock64();
       dbg_acc[5] += t1 - t0;
       tc_fence_after();
-#pragma unroll 1
-      for (int c0 = half * CW; c0 < BN; c0 += 2 * CW) {
-        if (p.epi_direct && all_al && n0 + c0 + CW <= p.N) {
-          // ---- direct path: two 16-row halves; every store instruction writes 8 rows x one 32-byte sector
-          const int g = lane >> 2, t2 = (lane & 3) * 2;
-#pragma unroll
-          for (int hr = 0; hr < 2; ++hr) {
-            uint32_t r8[8];
-            tmem_ld_16x256b_x2(tmem_base + acc * BN + c0 + ((uint32_t)(q * 32 + hr * 16) << 16), r8);
-            float2 add[2][2], res[2][2];
-#pragma unroll
-            for (int h8 = 0; h8 < 2; ++h8)
-#pragma unroll
-              for (int j = 0; j < 2; ++j) {
-                const int row = m0 + q * 32 + hr * 16 + h8 * 8 + g, col = n0 + c0 + 8 * j + t2;
-                float2 a2 = p.bias ? *reinterpret_cast<const float2*>(p.bias + col) : make_float2(0.f, 0.f);
-                if (p.pbias) {
-                  const float2 pp = *reinterpret_cast<const float2*>(p.pbias + pbd[hr * 2 + h8] + col);
-                  a2.x += pp.x; a2.y += pp.y;
-                }
-                add[h8][j] = a2;
-                res[h8][j] = (p.R && row < p.M) ? *reinterpret_cast<const float2*>(p.R + (size_t)row * p.ldr + col)
-                                                : make_float2(0.f, 0.f);
-              }
-#pragma unroll
-            for (int h8 = 0; h8 < 2; ++h8)
-#pragma unroll
-              for (int j = 0; j < 2; ++j) {
-                const int row = m0 + q * 32 + hr * 16 + h8 * 8 + g, col = n0 + c0 + 8 * j + t2;
-                float2 v = make_float2(__uint_as_float(r8[4 * j + 2 * h8]), __uint_as_float(r8[4 * j + 2 * h8 + 1]));
-                if (p.col0_bias_only && col == 0) v.x = 0.f;
-                v.x += add[h8][j].x; v.y += add[h8][j].y;
-                if (ACT == ACT_GELU) { v.x = (p.gelu_fit ? gelu_fit(v.x) : gelu_erf_tc_exact(v.x)); v.y = (p.gelu_fit ? gelu_fit(v.y) : gelu_erf_tc_exact(v.y)); }
-                if (ACT == ACT_RELU) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); }
-                v.x += res[h8][j].x; v.y += res[h8][j].y;
-                if (row < p.M) *reinterpret_cast<float2*>(p.C + (size_t)row * p.ldc + col) = v;
-              }
-          }
-          continue;
-        }
-        uint32_t r[CW];
-        tmem_ld16(tmem_base + acc * BN + c0 + ((uint32_t)(q * 32) << 16), r);
-        if (n0 + c0 >= p.N) continue;  // warp-uniform
-#pragma unroll
-        for (int j = 0; j < CW / 4; ++j)
-          *reinterpret_cast<float4*>(stg + lane * CP + 4 * j) =
-              make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
-                          __uint_as_float(r[4 * j + 3]));
-        __syncwarp();
-        const int col = n0 + c0 + cl;
-        if (all_al && n0 + c0 + CW <= p.N) {
-          // ---- fast path: whole sub-chunk inside N, everything 16-byte aligned
-          float4 rr[NIT], pp[NIT];
-          if (p.R) {
-#pragma unroll
-            for (int itr = 0; itr < NIT; ++itr) {
-              const int row = rbase + RPI * itr;
-              rr[itr] = row < p.M ? *reinterpret_cast<const float4*>(p.R + (size_t)row * p.ldr + col)
-                                  : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-          }
-          if (p.pbias) {
-#pragma unroll
-            for (int itr = 0; itr < NIT; ++itr) pp[itr] = *reinterpret_cast<const float4*>(p.pbias + pbo[itr] + col);
-          }
-          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p.bias) b4 = *reinterpret_cast<const float4*>(p.bias + col);
-#pragma unroll
-          for (int itr = 0; itr < NIT; ++itr) {
-            const int row = rbase + RPI * itr;
-            float4 v = *reinterpret_cast<const float4*>(stg + (rsub + RPI * itr) * CP + cl);
-            if (p.col0_bias_only && col == 0) v.x = 0.f;
-            if (p.pbias) { v.x += pp[itr].x; v.y += pp[itr].y; v.z += pp[itr].z; v.w += pp[itr].w; }
-            v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
-            if (ACT == ACT_GELU) { v.x = (p.gelu_fit ? gelu_fit(v.x) : gelu_erf_tc_exact(v.x)); v.y = (p.gelu_fit ? gelu_fit(v.y) : gelu_erf_tc_exact(v.y)); v.z = (p.gelu_fit ? gelu_fit(v.z) : gelu_erf_tc_exact(v.z)); v.w = (p.gelu_fit ? gelu_fit(v.w) : gelu_erf_tc_exact(v.w)); }
-            if (ACT == ACT_RELU) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-            if (p.R) { v.x += rr[itr].x; v.y += rr[itr].y; v.z += rr[itr].z; v.w += rr[itr].w; }
-            if (row < p.M) *reinterpret_cast<float4*>(p.C + (size_t)row * p.ldc + col) = v;
-          }
-        } else {
-          // ---- generic path (N tail / unaligned operands): scalar, guarded
-#pragma unroll 1
-          for (int itr = 0; itr < NIT; ++itr) {
-            const int row = rbase + RPI * itr;
-            if (row >= p.M) continue;
-#pragma unroll 1
-            for (int e = 0; e < 4; ++e) {
-              const int c = col + e;
-              if (c >= p.N) continue;
-              float x = stg[(rsub + RPI * itr) * CP + cl + e];
-              if (p.col0_bias_only && c == 0) x = 0.f;
-              if (p.pbias) x += p.pbias[(size_t)(row % p.pperiod) * p.N + c];
-              if (p.bias) x += p.bias[c];
-              if (ACT == ACT_GELU) x = (p.gelu_fit ? gelu_fit(x) : gelu_erf_tc_exact(x));
-              if (ACT == ACT_RELU) x = fmaxf(x, 0.f);
-              if (p.R) x += p.R[(size_t)row * p.ldr + c];
-              p.C[(size_t)row * p.ldc + c] = x;
-            }
-          }
-        }
-        __syncwarp();
-      }
+      float unused_cmax = 0.f;
+      epilogue_tile<BN, ACT, false>(p, tmem_base + acc * BN, m0, n0, q, half, lane, stg, all_al, pbo, pbd, 1.0f, unused_cmax);
       tc_fence_before();
       mbar_arrive(&tempty[acc]);
       dbg_acc[6] += clock64() - t1;

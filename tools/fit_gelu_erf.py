@@ -1,4 +1,4 @@
-"""Fit and check of the branch-free erf used by the GELU epilogues (gemm_tc.cu / gemm_f16.cu: gelu_fit).
+"""Fit and check of the branch-free erf used by the GELU epilogues (tc_common.cuh: gelu_fit).
 
 erf(t) = 1 - 2^(-t*g(t)), g = weighted minimax (Lawson) polynomial of -log2(erfc(t))/t on [0,4]; prints the max abs error
 of the fp32 evaluation for degrees 6..9, the degree-7 coefficients, and the error of the resulting fp32 GELU against

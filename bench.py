@@ -31,15 +31,19 @@ import torch  # noqa: E402
 
 from easydgl_b200 import synth  # noqa: E402
 
-WORKLOAD = "C2"
+WORKLOAD = "C2"       # default headline workload; --workload C3|C4|C5 selects BASELINE.json configs[2..4]
 NUM_INPUT_SETS = 4  # rotating distinct input batches
+# Per-GPU batch of each workload.  C2 / C3 name a single-GPU batch (4096).  C4 / C5 name a GLOBAL batch "across
+# 2/4/8 (8) B200": per GPU it is B/8, so the 8-GPU run is exactly the named configuration and smaller N are the
+# weak-scaling points of the same per-GPU work (--batch overrides; --scaling strong fixes the global batch instead).
+PER_GPU_BATCH = {"C1": 32, "C2": 4096, "C3": 4096, "C4": 8192 // 8, "C5": 16384 // 8}
 
 
-def workload_desc(cfg, B, n_gpus):
+def workload_desc(cfg, B, n_gpus, workload=None):
     return {
         "workload": "%s: %s d=%d L=%d items=%d B=%d/GPU h=%d blocks=%d E=%d; eval forward + mask_seen + top-%d"
-                    % (WORKLOAD, cfg.model, cfg.num_units, cfg.L, cfg.num_items, B, cfg.num_heads, cfg.num_blocks,
-                       cfg.num_events, cfg.topk),
+                    % (workload or WORKLOAD, cfg.model, cfg.num_units, cfg.L, cfg.num_items, B, cfg.num_heads,
+                       cfg.num_blocks, cfg.num_events, cfg.topk),
         "global_batch": B * n_gpus,
         "parallelism": "single GPU" if n_gpus == 1 else
         "batch-sharded encoder + column-sharded item table (%d shards); NCCL all-gather of [y|ids] rows, then "
@@ -51,15 +55,26 @@ def workload_desc(cfg, B, n_gpus):
 
 # ----------------------------------------------------------------------------- FLOP model
 def stage_flops(cfg, B):
-    """Algorithmic FLOPs (2*MAC) each stage's kernel performs per launch on B sequences."""
-    L, d, h, E, N1 = cfg.L, cfg.num_units, cfg.num_heads, cfg.num_events, cfg.num_rows
+    """Algorithmic FLOPs (2*MAC) each stage performs PER STEP on B sequences (summed over the stage's launches:
+    one per block, two for the CTSMA Q / KVT projections)."""
+    L, d, h, E, N1, nb = cfg.L, cfg.num_units, cfg.num_heads, cfg.num_events, cfg.num_rows, cfg.num_blocks
     dh = d // h
+    att = B * (6.0 * L * L * d + 2.0 * L * d * E * (dh + 2) + 2.0 * h * L * L * E)
+    if cfg.model == "CTSMA":  # SURVEY 8d: Q,K,V,T from [2d | d] inputs; FeedForward = two d x d conv1x1
+        return {
+            "qkvt_gemm": 2.0 * B * L * (2 * d) * 4 * d + (nb - 1) * 2.0 * B * L * d * 4 * d,
+            "attention": nb * att,
+            "ff1_gemm": nb * 2.0 * B * L * d * d,
+            "ff2_gemm": nb * 2.0 * B * L * d * d,
+            "logits_gemm": 2.0 * B * d * N1,
+        }
     return {
-        "qkvt_gemm": 2.0 * B * L * (d + E) * 4 * d,                  # folded block-0 QKVT dense
-        "attention": B * (6.0 * L * L * d + 2.0 * L * d * E * (dh + 2) + 2.0 * h * L * L * E),
-        "ao_gemm": 2.0 * B * L * d * d,
-        "ff1_gemm": 4.0 * B * L * d * d,
-        "ff2_gemm": 4.0 * B * L * d * d,
+        # block 0 runs the folded [d+E, 4d] kernel (DESIGN.md 3); later blocks a [d, 4d] one
+        "qkvt_gemm": 2.0 * B * L * (d + E) * 4 * d + (nb - 1) * 2.0 * B * L * d * 4 * d,
+        "attention": nb * att,
+        "ao_gemm": nb * 2.0 * B * L * d * d,
+        "ff1_gemm": nb * 4.0 * B * L * d * d,
+        "ff2_gemm": nb * 4.0 * B * L * d * d,
         "tr_gemm": 2.0 * B * L * d * d,
         "logits_gemm": 2.0 * B * d * N1,
     }
@@ -131,18 +146,21 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- CPU reference arm
-def cpu_reference(cfg, W, n_seqs, steps, warmup, threads):
-    """Times the fp32 CPU oracle (contracted mode, torch-CPU/MKL) on `n_seqs` sequences per step."""
+CPU_CHUNK = 128      # sequences per oracle call (the literal 4-D gate needs 1.3 MB per sequence and head at C2)
+CPU_SAMPLE = 256     # sequences per timed step of the reference arm / cpu_baseline leg
+
+
+def cpu_reference(cfg, W, n_seqs, steps, warmup, threads, literal=False, chunk=CPU_CHUNK):
+    """Times the fp32 CPU oracle (torch-CPU/MKL; contracted gate unless literal) on `n_seqs` sequences per step."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import easydgl_oracle as O
     torch.set_num_threads(threads)
     inp = synth.make_inputs(cfg, n_seqs, seed=synth.SEED + 100)
     ids, ts = inp["seqs_i"], inp["seqs_t"]
-    chunk = 128
 
     def one_step():
         for s in range(0, n_seqs, chunk):
-            logits = O.forward(ids[s:s + chunk], ts[s:s + chunk], W, cfg, dtype=torch.float32)
+            logits = O.forward(ids[s:s + chunk], ts[s:s + chunk], W, cfg, dtype=torch.float32, literal=literal)
             O.eval_topk(logits, ids[s:s + chunk], True, cfg.topk, rank_on="probs")
 
     with torch.no_grad():
@@ -155,27 +173,49 @@ def cpu_reference(cfg, W, n_seqs, steps, warmup, threads):
     return n_seqs * steps / dt, dt / steps
 
 
+def cpu_c1_legs(threads):
+    """the reference's own CPU-runnable case C1 (d=64, L=100, B=32) in literal mode (the two
+    [hB,L,L,E] tensors of temporal.py:309-313 materialised) and contracted mode, with 1 thread (what the reference
+    configures itself, main.py:167-168) and with all host threads.  A few seconds in total."""
+    cfg = synth.named_config("C1")
+    W = synth.make_weights(cfg, mode="reference")
+    out = {}
+    for name, lit, thr in (("c1_literal_1thread", True, 1), ("c1_contracted_1thread", False, 1),
+                           ("c1_literal_allthreads", True, threads), ("c1_contracted_allthreads", False, threads)):
+        sps, _ = cpu_reference(cfg, W, 32, 3, 1, thr, literal=lit, chunk=32)
+        out[name] = round(sps, 1)
+    torch.set_num_threads(threads)
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    cfg = synth.named_config(WORKLOAD)
+    wl = args.workload
+    cfg = synth.named_config(wl)
     W = synth.make_weights(cfg, mode="reference")
     threads = os.cpu_count() or 1
-    n_seqs = 256
-    sps, step_s = cpu_reference(cfg, W, n_seqs, args.steps, max(args.warmup, 1), threads)
-    sample = "%d sequences/step of the %s workload (2 chunks of 128), fp32 torch-CPU oracle, contracted gate" % (
-        n_seqs, WORKLOAD)
+    n_seqs = CPU_SAMPLE if cfg.L * cfg.num_units <= 200 * 128 else 32
+    sps, step_s = cpu_reference(cfg, W, n_seqs, args.steps, max(args.warmup, 1), threads, chunk=min(CPU_CHUNK, n_seqs))
+    sample = "%d sequences/step of the %s workload (%d chunk(s) of %d), fp32 torch-CPU oracle, contracted gate, %d threads" % (
+        n_seqs, wl, max(1, n_seqs // CPU_CHUNK), min(CPU_CHUNK, n_seqs), threads)
+    B = args.batch or PER_GPU_BATCH[wl]
+    conf = workload_desc(cfg, B, args.gpus, wl)
+    conf["reference_sample"] = ("this arm times %d sequences per step (seq/s is per sequence, so it is comparable to "
+                                "the GPU arm's B=%d/GPU steps)" % (n_seqs, B))
     line = {
         "impl": "reference", "metric": "sequences/sec", "value": sps, "unit": "seq/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_desc(cfg, synth.CONFIGS[WORKLOAD]["batch"], args.gpus),
+        "config": conf,
         "cpu_baseline": {"value": sps, "unit": "seq/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": sps, "unit": "seq/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "the reference needs tensorflow-gpu==2.3.4 (not installable here); this arm times oracle/, the "
                 "op-for-op CPU restatement of its forward path, with all host threads",
     }
+    if not args.no_c1:
+        line["cpu_baseline"]["c1_legs_seq_per_s"] = cpu_c1_legs(threads)
     _emit(args.out_fd, line)
     return 0
 
@@ -196,8 +236,11 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    cfg = synth.named_config(WORKLOAD)
-    B = args.batch or synth.CONFIGS[WORKLOAD]["batch"]
+    wl = args.workload
+    cfg = synth.named_config(wl)
+    B = args.batch or PER_GPU_BATCH[wl]
+    if args.scaling == "strong" and not args.batch:
+        B = max(1, synth.CONFIGS[wl]["batch"] // world)
     W = synth.make_weights(cfg, mode="reference")
     eng = E.Engine(cfg, W, max_batch=B, device=dev, shard_rank=rank if world > 1 else 0,
                    shard_world=world if world > 1 else 1)
@@ -300,15 +343,14 @@ def run_ours(args):
         stages = {}
         total_stage_ms = sum(v[0] for v in prof.values()) or 1.0
         for name, (sms, cnt) in prof.items():
-            avg = sms / cnt
-            rec = {"ms": round(avg, 4), "launches_per_step": cnt / args.steps, "share": round(sms / total_stage_ms, 4)}
-            scale = 1.0
-            if ranker is not None and name in ("logits_gemm", "topk"):
-                scale = 1.0  # per rank: G*B rows x N1/G columns = same FLOPs/bytes as unsharded
+            per_step = sms / args.steps  # all launches of the stage in one step (one per block; logits chunks)
+            rec = {"ms": round(per_step, 4), "launches_per_step": cnt / args.steps,
+                   "share": round(sms / total_stage_ms, 4)}
+            # sharded: per rank G*B rows x N1/G columns = the same FLOPs/bytes as unsharded
             if name in fl:
-                rec["tflops"] = round(fl[name] * scale / (avg * 1e-3) / 1e12, 3)
+                rec["tflops"] = round(fl[name] / (per_step * 1e-3) / 1e12, 3)
             if name in by:
-                rec["gbs"] = round(by[name] * scale / (avg * 1e-3) / 1e9, 1)
+                rec["gbs"] = round(by[name] / (per_step * 1e-3) / 1e9, 1)
             stages[name] = rec
         dom = max(prof.items(), key=lambda kv: kv[1][0])[0] if prof else None
         roof = None
@@ -319,7 +361,7 @@ def run_ours(args):
         except Exception:
             pass
         if dom in fl:
-            ach = fl[dom] / ((prof[dom][0] / prof[dom][1]) * 1e-3) / 1e12
+            ach = fl[dom] / ((prof[dom][0] / args.steps) * 1e-3) / 1e12
             roof = {"kernel": dom, "bound": "tensor", "achieved": round(ach, 3), "peak": tf_peak, "unit": "TFLOP/s",
                     "frac": round(ach / tf_peak, 5), "traffic": traffic, "peak_source": peak_src,
                     "note": "algorithmic fp32 FLOPs of the kernel / CUDA-event time; peak is the measured dense bf16 "
@@ -331,13 +373,14 @@ def run_ours(args):
                             "traffic = ncu dram bytes/launch (profiles/traffic.json)"}
         elif dom in by:
             hb = peaks.get("hbm_gbs", 6650.0)
-            ach = by[dom] / ((prof[dom][0] / prof[dom][1]) * 1e-3) / 1e9
+            ach = by[dom] / ((prof[dom][0] / args.steps) * 1e-3) / 1e9
             roof = {"kernel": dom, "bound": "hbm", "achieved": round(ach, 1), "peak": hb, "unit": "GB/s",
                     "frac": round(ach / hb, 4), "traffic": traffic, "peak_source": peak_src}
         line = {
             "metric": "sequences/sec", "value": value, "unit": "seq/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_desc(cfg, B, world),
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": args.scaling,
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_desc(cfg, B, world, wl),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "seq/s", "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
@@ -346,12 +389,14 @@ def run_ours(args):
         }
         if world == 1 and not args.no_cpu:
             threads = os.cpu_count() or 1
-            n_seqs = 256
-            sps, step_s = cpu_reference(cfg, W, n_seqs, args.cpu_steps, 1, threads)
+            n_seqs = CPU_SAMPLE if cfg.L * cfg.num_units <= 200 * 128 else 32
+            sps, step_s = cpu_reference(cfg, W, n_seqs, args.cpu_steps, 1, threads, chunk=min(CPU_CHUNK, n_seqs))
             line["cpu_baseline"] = {
                 "value": sps, "unit": "seq/s", "cores": threads, "kind": "port",
                 "sample": "%d steps x %d sequences of the %s workload (%.1f s), fp32 torch-CPU oracle, contracted gate"
-                          % (args.cpu_steps, n_seqs, WORKLOAD, step_s * args.cpu_steps)}
+                          % (args.cpu_steps, n_seqs, wl, step_s * args.cpu_steps)}
+            if not args.no_c1:
+                line["cpu_baseline"]["c1_legs_seq_per_s"] = cpu_c1_legs(threads)
         _emit(args.out_fd, line)
     if world > 1:
         dist.barrier()
@@ -383,7 +428,12 @@ def _main(out_fd):
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=0, help="override per-GPU batch (debug only)")
+    ap.add_argument("--workload", default=WORKLOAD, choices=["C2", "C3", "C4", "C5"],
+                    help="BASELINE.json configs[1..4]; C2 is the headline")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: fixed per-GPU batch (PER_GPU_BATCH); strong: the workload's batch divided over the ranks")
+    ap.add_argument("--no-c1", action="store_true", help="skip the C1 literal / 1-thread CPU legs")
+    ap.add_argument("--batch", type=int, default=0, help="override per-GPU batch")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-steps", type=int, default=20)
     ap.add_argument("--exchange", default="all_to_all", choices=["all_to_all", "all_gather", "p2p"],

@@ -277,9 +277,13 @@ int encode_easydgl(edgl_handle* h, const int64_t* ids, const float* ts, int B, f
                         nullptr, 0, st, true, w16(i, "qkvt_w", 0), am + AMAX_LN2));
     }
     AttnArgs a = attn_args(h, w, h->qkvt, h->kmask, h->spans, h->marks, cur, ldcur, h->p0, nullptr, B, false, true);
-    if (f16) a.out_amax = am + AMAX_ATT;
+    bool att_amax = false;
+    if (f16) { a.out_amax = am + AMAX_ATT; a.amax_published = &att_amax; }
     mark(h, ST_ATTENTION, st);
     EDGL_TRY(launch_attention(a, st));                                                   // temporal.py:412-447
+    // a fallback attention kernel (shape not covered at run time) does not publish max|O|: take it in a pass of
+    // its own rather than feed the scaled 3xFP16 attention-out GEMM a zero maximum
+    if (f16 && (h->f16_mask & 2) && !att_amax) EDGL_TRY(launch_absmax(h->p0, rows * d, am + AMAX_ATT, st));
     mark(h, ST_AO_GEMM, st);
     EDGL_TRY(dense_nk(h->p0, d, h->btT[i].at("ao_w"), d, F(w, "ao_b"), h->p1, d, rows, d, ACT_NONE, cur, ldcur, st, true,
                       w16(i, "ao_w", 1), am + AMAX_ATT));                                   // :113,116
@@ -667,7 +671,8 @@ int edgl_commit(edgl_handle* h, void* stream) {
       const auto& w = h->bt[i];
       const int cin = cin_of(h, i);
       if (easy) {
-        if (i > 0) EDGL_TRY(transposed(h->btT[i], "qkvt_w", F(w, "qkvt_w"), d, 4 * d));
+        // block 0's raw [3d,4d] kernel is only used by the layer-level entry point (the pipeline runs the folded one)
+        EDGL_TRY(transposed(h->btT[i], i > 0 ? "qkvt_w" : "qkvt_w_raw", F(w, "qkvt_w"), cin, 4 * d));
         EDGL_TRY(transposed(h->btT[i], "ao_w", F(w, "ao_w"), d, d));
         EDGL_TRY(transposed(h->btT[i], "ff1_w", F(w, "ff1_w"), d, 2 * d));
         EDGL_TRY(transposed(h->btT[i], "ff2_w", F(w, "ff2_w"), 2 * d, d));
@@ -899,10 +904,17 @@ int edgl_attention_layer(edgl_handle* h, int block, const float* queries, int Cq
   const auto& w = h->bt[block];
   const int cin = cin_of(h, block);
   EDGL_REQUIRE(Cq == cin, "queries width %d does not match the block's dense kernel (%d)", Cq, cin);
+  // projections: the tcgen05 GEMM the pipeline uses (default), or the exact-fp32 CUDA-core one (EDGL_LAYER_GEMM=simt)
+  const char* lg = getenv("EDGL_LAYER_GEMM");
+  const bool proj_tc = !(lg && lg[0] == 's');
   if (h->cfg.model == EDGL_MODEL_EASYDGL) {
     // BiMAU: `keys` and `causality` are ignored by the reference (temporal.py:404-429, Q15)
-    EDGL_TRY(dense(queries, Cq, F(w, "qkvt_w"), 4 * d, F(w, "qkvt_b"), h->qkvt, 4 * d, rows, 4 * d, Cq, ACT_NONE,
-                   nullptr, 0, st));
+    if (proj_tc)
+      EDGL_TRY(dense_nk(queries, Cq, h->btT[block].at(block > 0 ? "qkvt_w" : "qkvt_w_raw"), Cq, F(w, "qkvt_b"), h->qkvt,
+                        4 * d, rows, 4 * d, ACT_NONE, nullptr, 0, st));
+    else
+      EDGL_TRY(dense(queries, Cq, F(w, "qkvt_w"), 4 * d, F(w, "qkvt_b"), h->qkvt, 4 * d, rows, 4 * d, Cq, ACT_NONE,
+                     nullptr, 0, st));
     // bit 1 of `causality` selects T.MGAU (temporal.py:455-508): BiMAU without tf.linalg.set_diag
     AttnArgs a = attn_args(h, w, h->qkvt, kmask, intervals, marks, queries, Cq, out, lam, B, false,
                            (causality & 2) == 0);
@@ -910,9 +922,16 @@ int edgl_attention_layer(edgl_handle* h, int block, const float* queries, int Cq
   }
   if (!keys) return set_error(EDGL_EINVAL, "MAU needs keys");
   EDGL_REQUIRE(Ck == cin, "keys width %d does not match the block's dense kernels (%d)", Ck, cin);
-  EDGL_TRY(dense(queries, Cq, F(w, "q_w"), d, F(w, "q_b"), h->qkvt, 4 * d, rows, d, Cq, ACT_NONE, nullptr, 0, st));
-  EDGL_TRY(dense(keys, Ck, h->wkvt[block], 3 * d, h->bkvt[block], h->qkvt + d, 4 * d, rows, 3 * d, Ck, ACT_NONE,
-                 nullptr, 0, st));
+  if (proj_tc) {
+    EDGL_TRY(dense_nk(queries, Cq, h->btT[block].at("q_w"), Cq, F(w, "q_b"), h->qkvt, 4 * d, rows, d, ACT_NONE, nullptr,
+                      0, st));
+    EDGL_TRY(dense_nk(keys, Ck, h->btT[block].at("kvt_w"), Ck, h->bkvt[block], h->qkvt + d, 4 * d, rows, 3 * d, ACT_NONE,
+                      nullptr, 0, st));
+  } else {
+    EDGL_TRY(dense(queries, Cq, F(w, "q_w"), d, F(w, "q_b"), h->qkvt, 4 * d, rows, d, Cq, ACT_NONE, nullptr, 0, st));
+    EDGL_TRY(dense(keys, Ck, h->wkvt[block], 3 * d, h->bkvt[block], h->qkvt + d, 4 * d, rows, 3 * d, Ck, ACT_NONE,
+                   nullptr, 0, st));
+  }
   AttnArgs a = attn_args(h, w, h->qkvt, kmask, intervals, marks, queries, Cq, out, lam, B, (causality & 1) != 0, false);
   return launch_attention(a, st);
 }

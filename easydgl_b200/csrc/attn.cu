@@ -371,6 +371,7 @@ int launch_attention(const AttnArgs& a, cudaStream_t st) {
   EDGL_REQUIRE((a.ldq % 4 == 0) && (a.ldk % 4 == 0) && (a.ldv % 4 == 0) && (a.ldt % 4 == 0) &&
                    (a.ldo % 4 == 0) && (!a.R || a.ldr % 4 == 0),
                "attention: leading dimensions must be multiples of 4");
+  if (a.amax_published) *a.amax_published = false;
   if (a.B == 0) return 0;
   // tensor-core path (attn_mma.cuh) for the shapes it is instantiated for; EDGL_ATTN=simt forces the
   // CUDA-core kernel below (same results to fp32 rounding; used by the parity tests to cover both)
@@ -390,6 +391,7 @@ int launch_attention(const AttnArgs& a, cudaStream_t st) {
   // EDGL_ATTN=mma selects the 3xTF32 mma.sync kernel for every shape, as before.
   if (mode == 'f' || mode == 'd') {
     const int r = launch_attention_f16(a, st);
+    if (r == 0 && a.amax_published) *a.amax_published = a.out_amax != nullptr;
     if (r <= 0) return r;
   }
   if (!force_simt) {  // EDGL_ATTN=mma: the mma.sync kernel; EDGL_ATTN=simt: the CUDA-core kernel

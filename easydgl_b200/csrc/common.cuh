@@ -131,7 +131,8 @@ struct AttnArgs {
   int B, L, d, h, E;
   bool causal, diag_one;
   const void* mlp_pack = nullptr;  // attn_f16.cu: constants of the intensity MLP packed at commit, or null
-  unsigned int* out_amax = nullptr;  // attn_f16.cu only: running max |O| (amax_publish), or null
+  unsigned int* out_amax = nullptr;  // attn_f16.cu / attn_tc2.cu: running max |O| (amax_publish), or null
+  bool* amax_published = nullptr;    // host flag, set by launch_attention: did the kernel that ran publish out_amax?
 };
 int launch_attention(const AttnArgs& a, cudaStream_t st);
 // scaled 3xFP16 mma.sync kernel (attn_f16.cu): 0 = launched, 1 = shape not covered, <0 = error

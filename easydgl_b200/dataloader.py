@@ -48,14 +48,31 @@ def _crc32c_py(data: bytes) -> int:
 
 def crc32c(data) -> int:
     """CRC32C of a bytes-like object.  Anything longer than a frame header goes through the library's
-    host routine ``edgl_crc32c`` (include/easydgl_b200.h); the byte loop above is the independent
-    restatement the tests check it against."""
+    host routine ``edgl_crc32c`` (include/easydgl_b200.h) when the library is built; the byte loop above is
+    the independent restatement the tests check it against, and the fallback on a CPU-only preprocessing host
+    where libeasydgl_b200.so was never compiled (file framing is not the GPU hot path)."""
     mv = memoryview(data).cast("B")
     if len(mv) <= 16:
         return _crc32c_py(bytes(mv))
-    from . import _lib
+    lib = _native_lib()
+    if lib is None:
+        return _crc32c_py(bytes(mv))
     buf = np.frombuffer(mv, dtype=np.uint8)
-    return int(_lib.load().edgl_crc32c(buf.ctypes.data, buf.size, 0))
+    return int(lib.edgl_crc32c(buf.ctypes.data, buf.size, 0))
+
+
+_NATIVE = []
+
+
+def _native_lib():
+    """The shared library if it can be loaded, else None (cached)."""
+    if not _NATIVE:
+        try:
+            from . import _lib
+            _NATIVE.append(_lib.load())
+        except Exception:
+            _NATIVE.append(None)
+    return _NATIVE[0]
 
 
 def masked_crc32c(data: bytes) -> int:

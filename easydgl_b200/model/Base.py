@@ -114,9 +114,20 @@ class Sequential(object):
     def eval(self, features, labels, mask_seen=True):
         """Base.py:150-207.  Returns (metrics, topk_idx): the running means of H@{10,50,100} and
         N@{10,50,100} over every batch since ``reset_metrics()`` (tf.metrics.mean semantics), and this
-        batch's top-100 indices."""
+        batch's top-100 indices.
+
+        Deviation from the reference: the ranking is taken on the seen-masked LOGITS, not on
+        ``softmax(logits)`` (Base.py:164,181).  Softmax is monotone, so the order is the same wherever fp32
+        softmax is injective; where probabilities underflow to 0 (> ~88 nats below the row maximum) the
+        reference's ``top_k`` returns the lowest indices among the zeros, which is not reproduced.  The
+        cut-offs 100/50/10 are the reference's constants, so the engine must rank at least 100 items."""
         ids, ts = features['seqs_i'], features['seqs_t']
-        idx, _ = self._get_engine(ids.shape[0]).forward_topk(ids, ts, mask_seen)
+        eng = self._get_engine(ids.shape[0])
+        if eng.K < 100:
+            raise ValueError("eval() reports H/N@100 (Base.py:181): the engine must be built with topk >= 100 "
+                             "(got %d)" % eng.K)
+        idx, _ = eng.forward_topk(ids, ts, mask_seen)
+        idx = idx[:, :100]
         real = labels[:, -1:].to(idx.device).to(torch.int32)           # Base.py:169
         tp = (idx == real).to(torch.float64)                           # one-hot gather, Base.py:182-185
         gain = torch.tensor(1. / np.log2(np.arange(2, 100 + 2)), dtype=torch.float64, device=idx.device)

@@ -38,7 +38,15 @@ def shard_bounds(num_rows: int, rank: int, world: int):
 
 
 class ShardedRanker:
-    def __init__(self, engine, group=None, merge_fn=None, exchange="all_to_all"):
+    """``batch`` is the per-rank batch size every collective is sized for.  It must be the same on every rank,
+    so it is agreed ONCE: either passed to the constructor or taken from the first call, and in both cases
+    all-reduced (MAX) over the group - a collective every rank executes at the same point.  Later calls may pass
+    any ``B <= batch`` (e.g. the short last batch of ``InputReader``, drop_remainder=False): the rows are padded
+    with all-padding sequences (ids 0, ts 0) up to ``batch`` so that the exchanged buffers have identical
+    shapes on every rank, and the result is sliced back to ``B``.  A larger ``B`` raises instead of issuing a
+    size-mismatched collective (NCCL hang / wrong rows merged)."""
+
+    def __init__(self, engine, group=None, merge_fn=None, exchange="all_to_all", batch=None):
         if exchange not in ("all_to_all", "all_gather", "p2p"):
             raise ValueError("exchange must be 'all_to_all', 'all_gather' or 'p2p'")
         self.engine = engine
@@ -49,6 +57,29 @@ class ShardedRanker:
         self.merge_fn = merge_fn if merge_fn is not None else _merge_packed_cuda
         self._bufs = {}
         self._peer = None
+        self.batch = None
+        if batch is not None:
+            self._agree_batch(int(batch), engine.device)
+
+    def _agree_batch(self, B, device):
+        t = torch.tensor([B], dtype=torch.int64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        self.batch = int(t.item())
+        mb = getattr(self.engine, "max_batch", None)
+        if mb is not None and self.batch > mb:
+            raise ValueError("agreed per-rank batch %d exceeds the engine's max_batch %d" % (self.batch, mb))
+
+    def close(self):
+        if self._peer is not None:
+            self._peer.close()
+            self._peer = None
+        self._bufs = {}
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def _buf(self, name, shape, dtype, device):
         key = (name, tuple(shape), dtype, str(device))
@@ -60,13 +91,27 @@ class ShardedRanker:
 
     def forward_topk(self, seqs_i: torch.Tensor, seqs_t: torch.Tensor, mask_seen: bool = True):
         """Top-K (global item ids) for THIS rank's sequences. seqs_i [B,L] int64, seqs_t [B,ts_len]."""
+        Bin = int(seqs_i.shape[0])
+        if self.batch is None:
+            self._agree_batch(Bin, seqs_i.device)
+        if Bin > self.batch:
+            raise ValueError("batch %d exceeds the per-rank batch %d agreed for the exchange; build the "
+                             "ShardedRanker with batch=<largest per-rank batch>" % (Bin, self.batch))
+        if Bin < self.batch:  # pad with all-padding sequences; their candidates are dropped below
+            pad = self.batch - Bin
+            seqs_i = torch.cat([seqs_i, seqs_i.new_zeros((pad, seqs_i.shape[1]))])
+            seqs_t = torch.cat([seqs_t, seqs_t.new_zeros((pad, seqs_t.shape[1]))])
+        idx, val = self._forward_full(seqs_i, seqs_t, mask_seen)
+        return (idx, val) if Bin == self.batch else (idx[:Bin], val[:Bin])
+
+    def _forward_full(self, seqs_i, seqs_t, mask_seen):
         eng, G = self.engine, self.world
         B, L = seqs_i.shape
         d, K = eng.d, eng.K
         dev = seqs_i.device
         if self.exchange == "p2p":
-            if self._peer is None or self._peer.B != B:
-                self._peer = PeerExchange(eng, B, self.group)
+            if self._peer is None:
+                self._peer = PeerExchange(eng, B, self.group)  # sized once for the agreed batch
             return self._peer.forward_topk(seqs_i, seqs_t, mask_seen)
         # ---- exchange 1: packed [y | ids] rows (ids travel as raw bytes in fp32 lanes)
         y = eng.encode(seqs_i, seqs_t)

@@ -184,9 +184,12 @@ def test_intensity(name):
     assert_close(G.cpu(), rG, 1e-4, "G")
 
 
-@pytest.mark.parametrize("name", ["easy_a", "easy_b", "easy_c"])
-def test_bimau_layer(name):
-    """T.BiMAU.__call__ (temporal.py:404-452) incl. all-padding rows (Q8) and set_diag (Q4)."""
+@pytest.mark.parametrize("proj", ["tc", "simt"])
+@pytest.mark.parametrize("name", ["easy_a", "easy_b", "easy_c", "easy_d"])
+def test_bimau_layer(name, proj, monkeypatch):
+    """T.BiMAU.__call__ (temporal.py:404-452) incl. all-padding rows (Q8) and set_diag (Q4); QKVT projected by the
+    tcgen05 GEMM the pipeline uses (proj="tc") and by the exact-fp32 CUDA-core GEMM (proj="simt")."""
+    monkeypatch.setenv("EDGL_LAYER_GEMM", proj)
     cfg, inp, W = case(name, batch=6)
     eng = _engine(cfg, W, 6)
     W64 = O._cast(W, torch.float64)
@@ -199,9 +202,11 @@ def test_bimau_layer(name):
     assert_close(out.cpu(), rO, 1e-4, "BiMAU out")
 
 
+@pytest.mark.parametrize("proj", ["tc", "simt"])
 @pytest.mark.parametrize("name,causal", [("ctsma_a", True), ("ctsma_b", True), ("ctsma_b", False)])
-def test_mau_layer(name, causal):
+def test_mau_layer(name, causal, proj, monkeypatch):
     """T.MAU.__call__ (temporal.py:335-390): separate Q (from LN'd queries) and K/V/T (raw keys), causal mask."""
+    monkeypatch.setenv("EDGL_LAYER_GEMM", proj)
     cfg, inp, W = case(name, batch=6)
     eng = _engine(cfg, W, 6)
     W64 = O._cast(W, torch.float64)

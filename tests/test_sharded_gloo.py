@@ -87,6 +87,19 @@ def _worker(rank, world, port, q):
         idx2, _ = ranker.forward_topk(inp["seqs_i"], inp["seqs_t"], mask_seen=False)
         full.logits_topk(full.encode(inp["seqs_i"], inp["seqs_t"]), None, out)
         ok = ok and torch.equal(idx2, out[0])
+        # ragged batches (InputReader's short last batch): rank 1 passes 3 rows while rank 0 passes 5; the ranker
+        # pads to the batch agreed on the first call, so the collectives keep identical shapes on both ranks
+        nb = 5 if rank == 0 else 3
+        idx3, val3 = ranker.forward_topk(inp["seqs_i"][:nb], inp["seqs_t"][:nb], mask_seen=True)
+        out3 = (torch.empty(nb, 20, dtype=torch.int32), torch.empty(nb, 20))
+        full.logits_topk(full.encode(inp["seqs_i"][:nb], inp["seqs_t"][:nb]), inp["seqs_i"][:nb], out3)
+        ok = ok and idx3.shape[0] == nb and torch.equal(idx3, out3[0]) and torch.equal(val3, out3[1])
+        try:  # a batch larger than the agreed one must raise, not issue a mismatched collective
+            big = torch.cat([inp["seqs_i"], inp["seqs_i"]]), torch.cat([inp["seqs_t"], inp["seqs_t"]])
+            ranker.forward_topk(big[0], big[1])
+            ok = False
+        except ValueError:
+            pass
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()

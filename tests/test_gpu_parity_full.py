@@ -124,11 +124,11 @@ def test_q6_softplus_overflow_matches_reference():
     """lam = s * log(1 + exp(x / s)) (temporal.py:305-306) is the NAIVE form: it overflows to +inf for
     x/s > 88.72 in fp32, exactly like tf.exp / tf.log.  The kernels evaluate it with ex2 / lg2: same threshold."""
     import copy
-    for name in ("easy_d", "ctsma_b"):
+    for name, factor in (("easy_d", 22.0), ("ctsma_b", 50.0)):   # a minority of (row, head) pairs overflows
         cfg, inp, W = case(name, batch=6)
         W = copy.deepcopy(W)
         blk = W["blocks"][0]
-        blk["int_weight"] = blk["int_weight"] * 60.0          # pre-activations x of order +-1e2
+        blk["int_weight"] = blk["int_weight"] * factor        # pre-activations x of order +-1e2
         from easydgl_b200.engine import Engine
         eng = Engine(cfg, W, max_batch=6, device=DEV)
         res = {}
@@ -163,12 +163,14 @@ def test_q6_softplus_overflow_matches_reference():
         assert e < 1e-4, e
         # rows with an infinite intensity give inf * 0 = NaN in G (tf.matmul does the same): the set of non-finite
         # output rows must be the reference's
-        h = cfg.num_heads
-        bad_ref = ~torch.isfinite(out32).all(-1)           # [B, L]
-        bad_gpu = ~torch.isfinite(out).all(-1)
-        border = (~clear).any(-1).reshape(h, out.shape[0], out.shape[1]).any(0)   # lam is head-major [h*B, L, E]
-        assert torch.equal(bad_ref[~border], bad_gpu[~border]), "non-finite output rows differ from the fp32 reference"
-        ok = ~bad_ref & ~bad_gpu
+        h, dh = cfg.num_heads, cfg.num_units // cfg.num_heads
+        Bq, Lq = out.shape[0], out.shape[1]
+        per_head = lambda t: ~torch.isfinite(t.reshape(Bq, Lq, h, dh)).all(-1)      # [B, L, h]
+        bad_ref, bad_gpu = per_head(out32), per_head(out)
+        border = (~clear).any(-1).reshape(h, Bq, Lq).permute(1, 2, 0)               # lam is head-major [h*B, L, E]
+        assert int(bad_ref.sum()) > 0 and int((~bad_ref).sum()) > 0
+        assert torch.equal(bad_ref[~border], bad_gpu[~border]), "non-finite (row, head) set differs from the fp32 reference"
+        ok = (~bad_ref & ~bad_gpu).unsqueeze(-1).expand(Bq, Lq, h, dh).reshape(Bq, Lq, h * dh)
         eo = float((out[ok].double() - out64[ok]).abs().max() / out64[ok].abs().max())
         assert eo < 1e-4, eo
         _log({"test": "Q6_overflow", "case": name, "inf_lam": int(inf32.sum()), "nonfinite_rows": int(bad_ref.sum()),

@@ -72,6 +72,7 @@ struct edgl_handle {
   float* pbias0 = nullptr;     // EasyDGL block 0: [L,4d] = pos_embs @ W[d:2d] + b
   std::vector<float*> wkvt, bkvt;  // CTSMA: packed [Cin,3d], [3d]
   std::vector<unsigned char*> mlp_pack;  // per block: intensity-MLP constants for attn_f16.cu (null if not covered)
+  std::vector<unsigned char*> mlp_pack2;  // per block: the same constants in the tcgen05 operand layout of attn_tc2.cu
   // scaled 3xFP16 dense layers (gemm_f16.cu): fp16 hi/lo/scale copies of the K-major kernels, keyed like btT / mtT,
   // and the running activation maxima the producers publish (zeroed at the start of every encode)
   bool f16_gemm = false;
@@ -228,6 +229,8 @@ AttnArgs attn_args(const edgl_handle* h, const std::map<std::string, Tensor>& w,
   a.mlp_pack = nullptr;
   for (size_t i = 0; i < h->bt.size() && i < h->mlp_pack.size(); ++i)
     if (&h->bt[i] == &w) a.mlp_pack = h->mlp_pack[i];
+  for (size_t i = 0; i < h->bt.size() && i < h->mlp_pack2.size(); ++i)
+    if (&h->bt[i] == &w) a.mlp_pack2 = h->mlp_pack2[i];
   return a;
 }
 
@@ -487,7 +490,7 @@ int edgl_create(const edgl_config* cfg, edgl_handle** out) {
     // there (measured).  EDGL_F16_MASK=63 puts all six on it (parity-tested); EDGL_GEMM=tf32 none.
     const char* ge = getenv("EDGL_GEMM");
     const char* ae = getenv("EDGL_ATTN");
-    h->f16_gemm = easy && attention_f16_pack_bytes(h->dh, h->E) != 0 && h->L <= 208 && (!ae || ae[0] == 'f' || ae[0] == 'd') &&
+    h->f16_gemm = easy && attention_f16_pack_bytes(h->dh, h->E) != 0 && h->L <= 208 && (!ae || ae[0] == 'f' || ae[0] == 'd' || (ae[0] == 't' && ae[1] == 'c' && ae[2] == '2')) &&
                   !(ge && (ge[0] == 't' || ge[0] == 's'));
     if (const char* me = getenv("EDGL_F16_MASK")) h->f16_mask = atoi(me);
   }
@@ -648,6 +651,15 @@ int edgl_commit(edgl_handle* h, void* stream) {
       if (!h->mlp_pack[i]) EDGL_TRY(dev_alloc(h, &h->mlp_pack[i], pb));
       EDGL_TRY(launch_attention_f16_pack(F(w, "int_w"), F(w, "int_b"), F(w, "int_weight"), F(w, "int_scaling"), h->dh,
                                          E, h->mlp_pack[i], st));
+    }
+  }
+  if (const size_t pb = attention_tc2_pack_bytes(h->dh, E)) {
+    h->mlp_pack2.resize(h->cfg.num_blocks, nullptr);
+    for (int i = 0; i < h->cfg.num_blocks; ++i) {
+      const auto& w = h->bt[i];
+      if (!h->mlp_pack2[i]) EDGL_TRY(dev_alloc(h, &h->mlp_pack2[i], pb));
+      EDGL_TRY(launch_attention_tc2_pack(F(w, "int_w"), F(w, "int_b"), F(w, "int_weight"), F(w, "int_scaling"), h->dh,
+                                         E, h->mlp_pack2[i], st));
     }
   }
   // tf32 lo part of the owned rows of the tied item table (B operand of the logits GEMM); skipped above 2 GiB

@@ -364,6 +364,16 @@ static int launch_attention_stream_t(const AttnArgs& a, cudaStream_t st) {
 }
 
 int launch_attention(const AttnArgs& a, cudaStream_t st) {
+  static const char mode = [] {
+    const char* e = getenv("EDGL_ATTN");
+    if (!e) return 'd';
+    if (e[0] == 't' && e[1] == 'c' && e[2] == '2') return '2';
+    return e[0];
+  }();
+  return launch_attention_mode(a, st, mode);
+}
+
+int launch_attention_mode(const AttnArgs& a, cudaStream_t st, char mode) {
   EDGL_REQUIRE(a.d % a.h == 0, "num_units %d not divisible by num_heads %d", a.d, a.h);
   const int dh = a.d / a.h;
   EDGL_REQUIRE(a.E >= 1 && a.E <= 32, "num_events must be in [1,32] (got %d)", a.E);
@@ -375,11 +385,15 @@ int launch_attention(const AttnArgs& a, cudaStream_t st) {
   if (a.B == 0) return 0;
   // tensor-core path (attn_mma.cuh) for the shapes it is instantiated for; EDGL_ATTN=simt forces the
   // CUDA-core kernel below (same results to fp32 rounding; used by the parity tests to cover both)
-  static const char mode = [] {
-    const char* e = getenv("EDGL_ATTN");
-    return e ? e[0] : 'd';
-  }();
   const bool force_simt = mode == 's';
+  // EDGL_ATTN=tc2: the tcgen05 / TMA kernel with two items in flight (attn_tc2.cu; dh = 16, E = 16, L <= 112).  Parity
+  // green at fp32 level, but its serial per-item chain (five MMA round trips, 8 warps per item) runs at 1.61 ms at C2
+  // against 1.35 ms for the mma.sync kernel below, so it is opt-in (DESIGN.md section 4 has the per-phase cycle table)
+  if (mode == '2') {
+    const int r = launch_attention_tc2(a, st);
+    if (r == 0 && a.amax_published) *a.amax_published = a.out_amax != nullptr;
+    if (r <= 0) return r;
+  }
   // EDGL_ATTN=tc: the tcgen05 / TMEM kernel (attn_tc.cu; dh = 16, E = 16, L <= 128).  It passes the same parity
   // tests but, with one thread per query row, is latency-bound (2.4 ms at C2 against 1.35 ms for the default
   // attn_f16.cu); docs/attn_tc2_design.md describes the column-parallel successor.
@@ -387,9 +401,9 @@ int launch_attention(const AttnArgs& a, cudaStream_t st) {
     const int r = launch_attention_tc(a, st);
     if (r <= 0) return r;
   }
-  // default (and EDGL_ATTN=f16): the scaled 3xFP16 mma.sync kernel (attn_f16.cu; dh = 16, E = 16, L <= 208).
+  // next (and EDGL_ATTN=f16): the scaled 3xFP16 mma.sync kernel (attn_f16.cu; dh = 16, E = 16, L <= 208).
   // EDGL_ATTN=mma selects the 3xTF32 mma.sync kernel for every shape, as before.
-  if (mode == 'f' || mode == 'd') {
+  if (mode == 'f' || mode == 'd' || mode == '2') {
     const int r = launch_attention_f16(a, st);
     if (r == 0 && a.amax_published) *a.amax_published = a.out_amax != nullptr;
     if (r <= 0) return r;

@@ -133,6 +133,9 @@ struct AttnArgs {
   const void* mlp_pack = nullptr;  // attn_f16.cu: constants of the intensity MLP packed at commit, or null
   unsigned int* out_amax = nullptr;  // attn_f16.cu / attn_tc2.cu: running max |O| (amax_publish), or null
   bool* amax_published = nullptr;    // host flag, set by launch_attention: did the kernel that ran publish out_amax?
+  const void* mlp_pack2 = nullptr;   // attn_tc2.cu: constants of the intensity MLP (tcgen05 operand layout), or null
+  float* dbg = nullptr;              // attn_tc2.cu, debugging only: [items][8 phases][128 rows][256 cols] intermediates
+  long long* prof = nullptr;         // attn_tc2.cu, profiling only: [grid][2 slots][16] per-phase cycle counters
 };
 int launch_attention(const AttnArgs& a, cudaStream_t st);
 // scaled 3xFP16 mma.sync kernel (attn_f16.cu): 0 = launched, 1 = shape not covered, <0 = error
@@ -141,6 +144,14 @@ size_t attention_f16_pack_bytes(int dh, int E);  // 0 if the shape is not covere
 int launch_attention_f16_pack(const float* int_w, const float* int_b, const float* int_weight, const float* int_scaling,
                               int dh, int E, void* pack, cudaStream_t st);
 int launch_attention_tc(const AttnArgs& a, cudaStream_t st);
+// tcgen05 / TMA kernel with two items in flight and column-split rows (attn_tc2.cu): 0 = launched, 1 = not covered
+int launch_attention_tc2(const AttnArgs& a, cudaStream_t st);
+size_t attention_tc2_pack_bytes(int dh, int E);  // 0 if the shape is not covered
+int launch_attention_tc2_pack(const float* int_w, const float* int_b, const float* int_weight, const float* int_scaling,
+                              int dh, int E, void* pack, cudaStream_t st);
+// launch_attention with an explicit kernel choice: 'd' default, '2' tc2, 'f' f16 mma.sync, 't' tc (v1), 'm' mma tf32,
+// 's' CUDA cores
+int launch_attention_mode(const AttnArgs& a, cudaStream_t st, char mode);
 int launch_intensity(const float* H, const float* spans, const uint8_t* marks, const float* int_w,
                      const float* int_b, const float* int_weight, const float* int_scaling, int B, int L,
                      int h, int dh, int E, float* G, float* lam, cudaStream_t st);

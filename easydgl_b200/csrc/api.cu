@@ -84,6 +84,11 @@ struct edgl_handle {
   float* wfold0T = nullptr;                               // [4d, Ka]
   std::vector<std::map<std::string, float*>> btT;         // per block: name -> [N,K]
   std::map<std::string, float*> mtT;                      // model level (tr_w)
+  // LayerNorm folded into the tensor-core dense layers (LnEpi, common.cuh): EasyDGL, d % 16 == 0
+  bool ln_fuse = false;
+  float2* ln_parts = nullptr;                      // [rows][parts] row partial sums
+  float2 *ln_rs1 = nullptr, *ln_rs2 = nullptr, *ln_rs3 = nullptr;  // [max_batch] (mean, rstd)
+  float* tr_last = nullptr;                        // [max_batch, d] last rows of the transform layer
   // workspace (owned)
   float *xa = nullptr, *p0 = nullptr, *p1 = nullptr, *p2 = nullptr, *qkvt = nullptr, *spans = nullptr, *y = nullptr,
         *logits_ws = nullptr;
@@ -205,8 +210,9 @@ int dense(const float* A, int lda, const float* W, int ldw, const float* bias, f
 // dense layer with a K-major ([N,K]) kernel -> tensor-core path
 int dense_nk(const float* A, int lda, const float* Wt, int K, const float* bias, float* C, int ldc, long long M, int N,
              int act, const float* R, int ldr, cudaStream_t st, bool has_lo = true, const void* w16 = nullptr,
-             const unsigned int* a_amax = nullptr, unsigned int* c_amax = nullptr) {
+             const unsigned int* a_amax = nullptr, unsigned int* c_amax = nullptr, const LnEpi* ln = nullptr) {
   GemmArgs g;
+  if (ln) g.ln = *ln;
   g.W16 = w16; g.a_amax = w16 ? a_amax : nullptr; g.c_amax = c_amax;
   g.A = A; g.lda = lda; g.W = Wt; g.ldw = K; g.w_is_nk = true; g.C = C; g.ldc = ldc;
   if (has_lo) g.Wlo = Wt + (size_t)N * K;  // every K-major copy made by edgl_commit is followed by its tf32 lo part
@@ -287,6 +293,51 @@ int encode_easydgl(edgl_handle* h, const int64_t* ids, const float* ts, int B, f
     // a fallback attention kernel (shape not covered at run time) does not publish max|O|: take it in a pass of
     // its own rather than feed the scaled 3xFP16 attention-out GEMM a zero maximum
     if (f16 && (h->f16_mask & 2) && !att_amax) EDGL_TRY(launch_absmax(h->p0, rows * d, am + AMAX_ATT, st));
+    if (h->ln_fuse) {
+      // LayerNorm statistics from the producing GEMM's epilogue, applied by the consumers (LnEpi, common.cuh): no
+      // LayerNorm pass reads or writes the activations
+      const bool last = (i == h->cfg.num_blocks - 1);
+      const int np = ln_stats_parts(d);
+      LnEpi e_ao, e_ff1, e_ff2;
+      e_ao.stats = h->ln_parts; e_ao.L = L;
+      mark(h, ST_AO_GEMM, st);
+      EDGL_TRY(dense_nk(h->p0, d, h->btT[i].at("ao_w"), d, F(w, "ao_b"), h->p1, d, rows, d, ACT_NONE, cur, ldcur, st, true,
+                        nullptr, nullptr, nullptr, &e_ao));                                  // :113,116 (pre-LN)
+      mark(h, ST_LN_ATT, st);
+      EDGL_TRY(launch_ln_finalize(h->ln_parts, np, B, L, d, h->ln_rs1, nullptr, nullptr, nullptr, nullptr, nullptr, st));
+      e_ff1.a_rs = h->ln_rs1; e_ff1.a_g = F(w, "ao_ln_g"); e_ff1.a_b = F(w, "ao_ln_b"); e_ff1.L = L;
+      mark(h, ST_FF1_GEMM, st);
+      EDGL_TRY(dense_nk(h->p1, d, h->btT[i].at("ff1_w"), d, F(w, "ff1_b"), h->p2, 2 * d, rows, 2 * d, ACT_GELU,
+                        nullptr, 0, st, true, nullptr, nullptr, nullptr, &e_ff1));           // :116,120-121
+      e_ff2.r_rs = h->ln_rs1; e_ff2.r_g = F(w, "ao_ln_g"); e_ff2.r_b = F(w, "ao_ln_b"); e_ff2.L = L;
+      e_ff2.stats = h->ln_parts;
+      mark(h, ST_FF2_GEMM, st);
+      EDGL_TRY(dense_nk(h->p2, 2 * d, h->btT[i].at("ff2_w"), 2 * d, F(w, "ff2_b"), h->p0, d, rows, d, ACT_NONE, h->p1, d,
+                        st, true, nullptr, nullptr, nullptr, &e_ff2));                       // :125,128 (pre-LN)
+      mark(h, ST_LN_FF, st);
+      EDGL_TRY(launch_ln_finalize(h->ln_parts, np, B, L, d, h->ln_rs2, nullptr, nullptr, nullptr, nullptr, nullptr, st));
+      if (last) {
+        // transform + its LayerNorm (EasyDGL.py:138-139): only the last row of a sequence is used (:146), so the layer
+        // stores the last rows and the row statistics of all of them
+        LnEpi e_tr;
+        e_tr.a_rs = h->ln_rs2; e_tr.a_g = F(w, "ff_ln_g"); e_tr.a_b = F(w, "ff_ln_b"); e_tr.L = L;
+        e_tr.stats = h->ln_parts; e_tr.last_only = 1;
+        mark(h, ST_TR_GEMM, st);
+        EDGL_TRY(dense_nk(h->p0, d, h->mtT.at("tr_w"), d, F(h->mt, "tr_b"), h->tr_last, d, rows, d, ACT_GELU, nullptr, 0, st,
+                          true, nullptr, nullptr, nullptr, &e_tr));
+        mark(h, ST_LN_OUT, st);
+        EDGL_TRY(launch_ln_finalize(h->ln_parts, np, B, L, d, h->ln_rs3, h->tr_last, F(h->mt, "tr_ln_g"), F(h->mt, "tr_ln_b"),
+                                    y, (f16 && y == h->y) ? am + AMAX_Y : nullptr, st));
+        mark(h, ST_END, st);
+        return 0;
+      }
+      // more blocks follow: the next block reads LayerNorm(p0) three times (QKVT, both residuals): materialise it
+      EDGL_TRY(launch_layernorm(h->p0, F(w, "ff_ln_g"), F(w, "ff_ln_b"), B, L, d, h->p2, false, st,
+                                f16 ? am + AMAX_LN2 : nullptr));
+      cur = h->p2;
+      ldcur = d;
+      continue;
+    }
     mark(h, ST_AO_GEMM, st);
     EDGL_TRY(dense_nk(h->p0, d, h->btT[i].at("ao_w"), d, F(w, "ao_b"), h->p1, d, rows, d, ACT_NONE, cur, ldcur, st, true,
                       w16(i, "ao_w", 1), am + AMAX_ATT));                                   // :113,116
@@ -481,6 +532,19 @@ int edgl_create(const edgl_config* cfg, edgl_handle** out) {
   EDGL_ALLOC(h->kmask, rows);
   EDGL_ALLOC(h->y, (long long)cfg->max_batch * d);
   EDGL_ALLOC(h->amax, AMAX_COUNT);
+  {
+    // LayerNorm folded into the tensor-core dense layers: EasyDGL, d a multiple of 16, tensor-core GEMMs in use
+    const char* ge = getenv("EDGL_GEMM");
+    const char* le = getenv("EDGL_LN_FUSE");
+    h->ln_fuse = easy && d % 16 == 0 && !(ge && ge[0] == 's') && !(le && le[0] == '0');
+    if (h->ln_fuse) {
+      EDGL_ALLOC(h->ln_parts, rows * ln_stats_parts(d));
+      EDGL_ALLOC(h->ln_rs1, cfg->max_batch);
+      EDGL_ALLOC(h->ln_rs2, cfg->max_batch);
+      EDGL_ALLOC(h->ln_rs3, cfg->max_batch);
+      EDGL_ALLOC(h->tr_last, (long long)cfg->max_batch * d);
+    }
+  }
   {
     // The scaled 3xFP16 dense layers (gemm_f16.cu) need every activation's running maximum from its producer, and
     // the attention producer that publishes one is attn_f16.cu: EasyDGL with dh = 16, E = 16, L <= 208 and the default

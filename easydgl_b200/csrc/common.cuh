@@ -60,6 +60,29 @@ __device__ __forceinline__ void amax_publish(unsigned int* slot, float warp_loca
 // ------------------------------------------------------------------ kernel launchers (one per .cu)
 enum Act { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2 };
 
+// LayerNorm folded into the tensor-core dense layers (Base.layernorm over (L, C) jointly, Base.py:12-67): the producer
+// of a tensor emits per-row partial sums in its epilogue, launch_ln_finalize turns them into (mean, rstd) per
+// sequence, and the consumers normalise on the fly - no LayerNorm pass reads or writes the activations:
+//  * as the A operand: the splitter warps, which touch every A element in shared memory anyway, write
+//    (x - mean) rstd gamma + beta in place before they split it;
+//  * as the residual: the epilogue applies the same formula to the residual rows it loads.
+struct LnEpi {
+  const float2* a_rs = nullptr;  // per-sequence (mean, rstd) of the LayerNorm applied to A
+  const float* a_g = nullptr;    // [K] gamma
+  const float* a_b = nullptr;    // [K] beta
+  const float2* r_rs = nullptr;  // per-sequence (mean, rstd) of the LayerNorm applied to the residual rows
+  const float* r_g = nullptr;    // [N] gamma
+  const float* r_b = nullptr;    // [N] beta
+  float2* stats = nullptr;       // [M][2 * ceil(N / BN)] row partial (sum, sum of squares) of the stored values
+  int L = 1;                     // rows per sequence
+  int last_only = 0;             // store only the rows with row % L == L-1, at C[(row / L) * ldc]
+  bool any() const { return a_rs || r_rs || stats || last_only; }
+};
+int ln_stats_parts(int N);  // number of partials per row the tensor-core GEMM writes for N columns
+// (mean, rstd)[b] from the row partials of B sequences of L rows x C columns; optionally y[b] = LN(x_last[b]) with
+// x_last [B, C] (the stored last rows), gamma, beta
+int launch_ln_finalize(const float2* parts, int nparts, int B, int L, int C, float2* rs, const float* x_last,
+                       const float* gamma, const float* beta, float* y, unsigned int* y_amax, cudaStream_t st);
 // C[M,N] (ldc) = act(A[M,K] (lda) @ W + bias[N] + pbias[(m % pperiod), N]) + R[M,N] (ldr)
 // W is [K,N] (ldw) row-major, or, if w_is_nk, [N,K] (ldw) row-major (C = A @ W^T).
 // col0_const: if non-null-flag set, global column (col_offset+0)==0 gets exactly bias (acc ignored)
@@ -79,6 +102,7 @@ struct GemmArgs {
   const float* R = nullptr; int ldr = 0;       // residual or null
   int act = ACT_NONE;
   bool zero_wrow0 = false;  // w_is_nk only: treat W row 0 (= output column 0) as all-zero (zero_pad table)
+  LnEpi ln;                 // tensor-core path only (3xTF32 kernel): fused LayerNorm pieces, see above
 };
 int launch_gemm(const GemmArgs& a, cudaStream_t st);
 bool gemm_tc_supported(const GemmArgs& a);

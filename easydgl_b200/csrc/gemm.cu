@@ -231,6 +231,10 @@ int launch_gemm(const GemmArgs& a, cudaStream_t st) {
     const char* e = getenv("EDGL_GEMM");
     return e && e[0] == 's';
   }();
+  if (a.ln.any()) {  // fused LayerNorm pieces exist in the 3xTF32 tensor-core kernel only (callers check EDGL_GEMM)
+    EDGL_REQUIRE(gemm_tc_supported(a), "gemm: a fused-LayerNorm dense layer needs the tensor-core path");
+    return launch_gemm_tc(a, st);
+  }
   if (!force_simt && gemm_f16_supported(a)) return launch_gemm_f16(a, st);  // scaled 3xFP16 on kind::f16
   if (!force_simt && gemm_tc_supported(a)) return launch_gemm_tc(a, st);
   const int ntn = cdiv(a.N, BN);

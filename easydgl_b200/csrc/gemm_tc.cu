@@ -78,6 +78,7 @@ struct Params {
   int act;
   int col0_bias_only;  // tied zero-padded table: column 0 is exactly the bias (coding.py:56-57)
   int ntn, num_tiles, kblocks;
+  LnEpi ln;        // fused LayerNorm pieces of the epilogue (common.cuh); all null = off
   int epi_direct;  // epilogue stores rows straight from TMEM fragments (no shared-memory transpose)
   int has_blo;  // W_lo = W - tf32(W) is pre-computed in global memory (weights are constant after commit): TMA brings
                 // it in like W and the splitter warps only split the activations
@@ -90,10 +91,11 @@ struct Smem {
   static constexpr int B_BYTES = BN * BK * 4;
   static constexpr int STAGE = 2 * A_BYTES + 2 * B_BYTES;
   static constexpr int STAGES = (BN == 256) ? 2 : 3;
-  static constexpr int BYTES = STAGES * STAGE + 1024 /*align*/ + 256 /*barriers*/ + 8 * 32 * CP * 4 /*epilogue*/;
+  static constexpr int LN_BYTES = 2 * 512 * 4;  // gamma / beta of a LayerNorm folded into A (K <= 512)
+  static constexpr int BYTES = STAGES * STAGE + 1024 /*align*/ + 256 /*barriers*/ + 8 * 32 * CP * 4 /*epilogue*/ + LN_BYTES;
 };
 
-template <int BN, int ACT>
+template <int BN, int ACT, int LNF>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                const __grid_constant__ CUtensorMap mapBlo, Params p) {
@@ -204,6 +206,64 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     // ------------------------------------------------------------------ splitters: lo = x - tf32(x)
     const int t = threadIdx.x - 384;  // 0..127
     uint32_t it = 0;
+    auto lo4 = [](float4 v) {
+      float4 r;
+      r.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+      r.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+      r.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+      r.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+      return r;
+    };
+    if constexpr ((LNF & LN_A) != 0) {
+      // A = LayerNorm(x) (LnEpi): thread t owns row t of the tile and rewrites it in place as
+      // (x - mean) rstd gamma + beta before taking the lo part.  gamma / beta of the whole K range sit in shared
+      // memory (zero beyond K, where TMA has zero-filled W as well); 16-byte chunk c of a 128-byte swizzle row is
+      // stored at c ^ (row % 8), so the eight rows of a quarter-warp hit eight different bank groups.
+      float* gb = reinterpret_cast<float*>(base + S * SM::STAGE + 256 + 8 * 32 * CP * 4);  // [2][KB * BK]
+      const int kpad = KB * BK;
+      for (int i = t; i < kpad; i += 128) {
+        gb[i] = i < p.K ? p.ln.a_g[i] : 0.f;
+        gb[kpad + i] = i < p.K ? p.ln.a_b[i] : 0.f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const uint32_t rowoff = (uint32_t)((t >> 3) * 1024 + (t & 7) * 128), sx = (uint32_t)(t & 7);
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int row = (tile / p.ntn) * BM + t;
+        float rs = 1.f, nm = 0.f;
+        if (row < p.M) {
+          const float2 mr = p.ln.a_rs[row / p.ln.L];
+          rs = mr.y;
+          nm = -mr.x * mr.y;
+        }
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int s = it % S;
+          mbar_wait(&full[s], (it / S) & 1);
+          uint8_t* a = stA(s) + rowoff;
+          uint8_t* al = stAlo(s) + rowoff;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const uint32_t o = ((uint32_t)c ^ sx) << 4;
+            float4 v = *reinterpret_cast<const float4*>(a + o);
+            const float4 g4 = *reinterpret_cast<const float4*>(gb + kb * BK + c * 4);
+            const float4 e4 = *reinterpret_cast<const float4*>(gb + kpad + kb * BK + c * 4);
+            v.x = fmaf(fmaf(v.x, rs, nm), g4.x, e4.x);
+            v.y = fmaf(fmaf(v.y, rs, nm), g4.y, e4.y);
+            v.z = fmaf(fmaf(v.z, rs, nm), g4.z, e4.z);
+            v.w = fmaf(fmaf(v.w, rs, nm), g4.w, e4.w);
+            *reinterpret_cast<float4*>(a + o) = v;
+            *reinterpret_cast<float4*>(al + o) = lo4(v);
+          }
+          if (!p.has_blo) {
+            const float4* b = reinterpret_cast<const float4*>(stB(s));
+            float4* bl = reinterpret_cast<float4*>(stBlo(s));
+#pragma unroll 4
+            for (int i = t; i < SM::B_BYTES / 16; i += 128) bl[i] = lo4(b[i]);
+          }
+          fence_proxy_async();
+          mbar_arrive(&split[s]);
+        }
+      }
+    } else {
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       for (int kb = 0; kb < KB; ++kb, ++it) {
         const int s = it % S;
@@ -215,14 +275,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         float4* al = reinterpret_cast<float4*>(stAlo(s));
         const float4* b = reinterpret_cast<const float4*>(stB(s));
         float4* bl = reinterpret_cast<float4*>(stBlo(s));
-        auto lo4 = [](float4 v) {
-          float4 r;
-          r.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
-          r.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
-          r.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
-          r.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
-          return r;
-        };
 #pragma unroll 4
         for (int i = t; i < SM::A_BYTES / 16; i += 128) al[i] = lo4(a[i]);
         if (!p.has_blo) {
@@ -233,6 +285,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         mbar_arrive(&split[s]);
         dbg_acc[4] += clock64() - t1;
       }
+    }
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue
@@ -279,7 +332,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       dbg_acc[5] += t1 - t0;
       tc_fence_after();
       float unused_cmax = 0.f;
-      epilogue_tile<BN, ACT, false>(p, tmem_base + acc * BN, m0, n0, q, half, lane, stg, all_al, pbo, pbd, 1.0f, unused_cmax);
+      epilogue_tile<BN, ACT, false, (LNF & ~LN_A)>(p, tmem_base + acc * BN, m0, n0, q, half, lane, stg, all_al, pbo, pbd, 1.0f, unused_cmax);
       tc_fence_before();
       mbar_arrive(&tempty[acc]);
       dbg_acc[6] += clock64() - t1;
@@ -299,6 +352,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 }
 
 }  // namespace tc
+
+int ln_stats_parts(int N) { return 2 * cdiv(N, N > 128 ? 256 : 128); }
 
 // Can this GEMM go through the tensor-core kernel?  (W must be [N,K] K-major.)
 bool gemm_tc_supported(const GemmArgs& a) {
@@ -341,6 +396,19 @@ int launch_gemm_tc(const GemmArgs& a, cudaStream_t st) {
     return e ? e[0] : 'a';
   }();
   p.epi_direct = epi_mode == 'd' ? 1 : epi_mode == 's' ? 0 : (a.R == nullptr && a.pbias == nullptr) ? 1 : 0;
+  p.ln = a.ln;
+  int lnf = 0;
+  if (a.ln.any()) {
+    // the fused LayerNorm pieces live in the staged fast path of the epilogue (and in the splitter warps) only
+    EDGL_REQUIRE(a.N % 16 == 0 && a.ldc % 4 == 0 && (!a.R || a.ldr % 4 == 0) && a.ln.L >= 1 && a.K <= 512 &&
+                     (reinterpret_cast<uintptr_t>(a.C) & 15) == 0 && (!a.R || (reinterpret_cast<uintptr_t>(a.R) & 15) == 0) &&
+                     (!a.bias || (reinterpret_cast<uintptr_t>(a.bias) & 15) == 0) && !a.pbias,
+                 "gemm_tc: fused LayerNorm needs N %% 16 == 0, K <= 512 and 16-byte aligned operands");
+    EDGL_REQUIRE(!a.ln.a_rs || (a.ln.a_g && a.ln.a_b), "gemm_tc: LayerNorm on A needs gamma and beta");
+    EDGL_REQUIRE(!a.ln.r_rs || (a.R && a.ln.r_g && a.ln.r_b), "gemm_tc: LayerNorm on the residual needs R, gamma, beta");
+    p.epi_direct = 0;
+    lnf = (a.ln.a_rs ? LN_A : 0) | (a.ln.r_rs ? LN_RES : 0) | (a.ln.stats ? LN_STATS : 0) | (a.ln.last_only ? LN_LAST : 0);
+  }
   p.ntn = cdiv(a.N, bn);
   const long long ntm = cdiv(a.M, BM);
   EDGL_REQUIRE(ntm * p.ntn < (1ll << 31), "gemm_tc: too many tiles");
@@ -355,9 +423,36 @@ int launch_gemm_tc(const GemmArgs& a, cudaStream_t st) {
     cudaMemsetAsync(dbg_buf, 0, 8 * 256 * sizeof(long long), st);
     p.dbg = dbg_buf;
   }
+#define EDGL_TC_LAUNCH_L(BNV, ACTV, LNV)                                                                       \
+  {                                                                                                            \
+    auto kern = gemm_tc_kernel<BNV, ACTV, LNV>;                                                                \
+    EDGL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BNV>::BYTES));      \
+    kern<<<grid, NTHREADS, Smem<BNV>::BYTES, st>>>(mapA, mapB, mapBlo, p);                                     \
+  }
+  // the fused-LayerNorm combinations the EasyDGL block tail uses (api.cu): attention-out (statistics), FF1 (A is a
+  // LayerNorm; GELU), FF2 (residual is a LayerNorm; statistics), transform (A is a LayerNorm; GELU; statistics; last rows)
+  if (lnf != 0) {
+    bool ok = true;
+    if (bn == 256) {
+      if (lnf == LN_STATS && a.act == ACT_NONE) EDGL_TC_LAUNCH_L(256, ACT_NONE, LN_STATS)
+      else if (lnf == LN_A && a.act == ACT_GELU) EDGL_TC_LAUNCH_L(256, ACT_GELU, LN_A)
+      else if (lnf == (LN_RES | LN_STATS) && a.act == ACT_NONE) EDGL_TC_LAUNCH_L(256, ACT_NONE, LN_RES | LN_STATS)
+      else if (lnf == (LN_A | LN_STATS | LN_LAST) && a.act == ACT_GELU) EDGL_TC_LAUNCH_L(256, ACT_GELU, LN_A | LN_STATS | LN_LAST)
+      else ok = false;
+    } else {
+      if (lnf == LN_STATS && a.act == ACT_NONE) EDGL_TC_LAUNCH_L(128, ACT_NONE, LN_STATS)
+      else if (lnf == LN_A && a.act == ACT_GELU) EDGL_TC_LAUNCH_L(128, ACT_GELU, LN_A)
+      else if (lnf == (LN_RES | LN_STATS) && a.act == ACT_NONE) EDGL_TC_LAUNCH_L(128, ACT_NONE, LN_RES | LN_STATS)
+      else if (lnf == (LN_A | LN_STATS | LN_LAST) && a.act == ACT_GELU) EDGL_TC_LAUNCH_L(128, ACT_GELU, LN_A | LN_STATS | LN_LAST)
+      else ok = false;
+    }
+    EDGL_REQUIRE(ok, "gemm_tc: fused-LayerNorm combination %d with activation %d is not instantiated", lnf, a.act);
+    EDGL_LAUNCH_CHECK();
+    return 0;
+  }
 #define EDGL_TC_LAUNCH(BNV, ACTV)                                                                              \
   {                                                                                                            \
-    auto kern = gemm_tc_kernel<BNV, ACTV>;                                                                     \
+    auto kern = gemm_tc_kernel<BNV, ACTV, 0>;                                                                  \
     EDGL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BNV>::BYTES));      \
     kern<<<grid, NTHREADS, Smem<BNV>::BYTES, st>>>(mapA, mapB, mapBlo, p);                                            \
   }

@@ -77,6 +77,59 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   if (out_amax) amax_publish(out_amax, omax, threadIdx.x & 31);
 }
 
+// ---- LayerNorm folded into the tensor-core dense layers (LnEpi, common.cuh)
+// One warp per sequence: the L * nparts row partials are summed in a fixed order in double precision;
+// var = E[x^2] - mean^2 (clamped at 0), rstd = 1 / sqrt(var + 1e-12)  (Base.py:51-56).  Optionally the warp also
+// writes y = LN(x_last) for the sequence's stored last row (EasyDGL.py:139,146).
+__global__ void __launch_bounds__(256) ln_finalize_kernel(const float2* __restrict__ parts, int nparts, int B, int L,
+                                                          int C, float2* __restrict__ rs,
+                                                          const float* __restrict__ x_last,
+                                                          const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, float* __restrict__ y,
+                                                          unsigned int* __restrict__ y_amax) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= B) return;
+  const float2* p = parts + (size_t)warp * L * nparts;
+  const int n = L * nparts;
+  double s = 0.0, q = 0.0;
+  for (int i = lane; i < n; i += 32) {
+    const float2 v = p[i];
+    s += (double)v.x;
+    q += (double)v.y;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  const double cnt = (double)L * (double)C;
+  const double mean = s / cnt;
+  double var = q / cnt - mean * mean;
+  if (!(var > 0.0)) var = 0.0;
+  const float meanf = (float)mean;
+  const float rstd = (float)(1.0 / sqrt(var + 1e-12));
+  if (lane == 0) rs[warp] = make_float2(meanf, rstd);
+  if (y) {
+    float omax = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      const float inv = rstd * gamma[c];
+      const float o = x_last[(size_t)warp * C + c] * inv + (beta[c] - meanf * inv);
+      y[(size_t)warp * C + c] = o;
+      omax = fmaxf(omax, fabsf(o));
+    }
+    if (y_amax) amax_publish(y_amax, omax, lane);
+  }
+}
+
+int launch_ln_finalize(const float2* parts, int nparts, int B, int L, int C, float2* rs, const float* x_last,
+                       const float* gamma, const float* beta, float* y, unsigned int* y_amax, cudaStream_t st) {
+  if (B == 0) return 0;
+  ln_finalize_kernel<<<cdiv((long long)B * 32, 256), 256, 0, st>>>(parts, nparts, B, L, C, rs, x_last, gamma, beta, y,
+                                                                     y_amax);
+  EDGL_LAUNCH_CHECK();
+  return 0;
+}
+
 int launch_layernorm(const float* x, const float* gamma, const float* beta, int B, int L, int C, float* out,
                      bool last_only, cudaStream_t st, unsigned int* out_amax) {
   EDGL_REQUIRE(C % 4 == 0, "layernorm: channel count must be a multiple of 4 (got %d)", C);

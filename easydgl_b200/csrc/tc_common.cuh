@@ -109,7 +109,12 @@ __device__ __forceinline__ float gelu_erf_exact(float x) {
 //    every load of a chunk is issued before the first store (C and R may alias as far as the compiler knows);
 //  * direct (p.epi_direct): 16x256b fragments, rows stored sector by sector from registers, no shared memory.
 // SCALED (gemm_f16.cu): the accumulator is multiplied by `inv` (1 / (sa * sw)) first and max|C| is tracked in cmax.
-template <int BN, int ACT, bool SCALED, class P>
+// LNF (bit mask, gemm_tc.cu only): fused LayerNorm pieces of LnEpi (common.cuh) - LN_RES: the residual rows are
+// LayerNorm(R); LN_STATS: per-row partial sums of the stored values; LN_LAST: store only the last row of every
+// sequence.  (LN_A, the normalisation of the A operand, lives in the splitter warps.)
+constexpr int LN_A = 1, LN_RES = 2, LN_STATS = 4, LN_LAST = 8;
+
+template <int BN, int ACT, bool SCALED, int LNF = 0, class P>
 __device__ __forceinline__ void epilogue_tile(const P& p, uint32_t tmem_acc, int m0, int n0, int q, int half, int lane,
                                               float* stg, bool all_al, const int (&pbo)[4], const int (&pbd)[4], float inv,
                                               float& cmax) {
@@ -124,9 +129,28 @@ __device__ __forceinline__ void epilogue_tile(const P& p, uint32_t tmem_acc, int
     if constexpr (SCALED) x *= inv;
     return x;
   };
+  // fused LayerNorm pieces: (mean, rstd) of the sequence each of this lane's rows belongs to, the rows' running
+  // partial sums, and the output row of a last-row-only store (-1: not a last row)
+  float2 lnr[NIT];
+  float st_s[NIT], st_q[NIT];
+  int lnlast[NIT];
+  if constexpr (LNF != 0) {
+#pragma unroll
+    for (int itr = 0; itr < NIT; ++itr) {
+      lnr[itr] = make_float2(0.f, 1.f);
+      st_s[itr] = st_q[itr] = 0.f;
+      lnlast[itr] = -1;
+      const int row = rbase + RPI * itr;
+      if (row < p.M) {
+        const int sq = row / p.ln.L;
+        if constexpr ((LNF & LN_RES) != 0) lnr[itr] = p.ln.r_rs[sq];
+        if (row - sq * p.ln.L == p.ln.L - 1) lnlast[itr] = sq;
+      }
+    }
+  }
 #pragma unroll 1
   for (int c0 = half * CW; c0 < BN; c0 += 2 * CW) {
-    if (p.epi_direct && all_al && n0 + c0 + CW <= p.N) {
+    if (LNF == 0 && p.epi_direct && all_al && n0 + c0 + CW <= p.N) {
       // ---- direct path: two 16-row halves; every store instruction writes 8 rows x one 32-byte sector
       const int g = lane >> 2, t2 = (lane & 3) * 2;
 #pragma unroll
@@ -186,6 +210,18 @@ __device__ __forceinline__ void epilogue_tile(const P& p, uint32_t tmem_acc, int
           rr[itr] = row < p.M ? *reinterpret_cast<const float4*>(p.R + (size_t)row * p.ldr + col)
                               : make_float4(0.f, 0.f, 0.f, 0.f);
         }
+        if constexpr ((LNF & LN_RES) != 0) {  // the residual is LayerNorm(R): (R - mean) rstd gamma + beta
+          const float4 g4 = *reinterpret_cast<const float4*>(p.ln.r_g + col);
+          const float4 e4 = *reinterpret_cast<const float4*>(p.ln.r_b + col);
+#pragma unroll
+          for (int itr = 0; itr < NIT; ++itr) {
+            const float rs = lnr[itr].y, nm = -lnr[itr].x * lnr[itr].y;
+            rr[itr].x = fmaf(fmaf(rr[itr].x, rs, nm), g4.x, e4.x);
+            rr[itr].y = fmaf(fmaf(rr[itr].y, rs, nm), g4.y, e4.y);
+            rr[itr].z = fmaf(fmaf(rr[itr].z, rs, nm), g4.z, e4.z);
+            rr[itr].w = fmaf(fmaf(rr[itr].w, rs, nm), g4.w, e4.w);
+          }
+        }
       }
       if (p.pbias) {
 #pragma unroll
@@ -204,7 +240,15 @@ __device__ __forceinline__ void epilogue_tile(const P& p, uint32_t tmem_acc, int
         if (ACT == ACT_RELU) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
         if (p.R) { v.x += rr[itr].x; v.y += rr[itr].y; v.z += rr[itr].z; v.w += rr[itr].w; }
         if (row < p.M) {
-          *reinterpret_cast<float4*>(p.C + (size_t)row * p.ldc + col) = v;
+          if constexpr ((LNF & LN_STATS) != 0) {
+            st_s[itr] += (v.x + v.y) + (v.z + v.w);
+            st_q[itr] += fmaf(v.x, v.x, v.y * v.y) + fmaf(v.z, v.z, v.w * v.w);
+          }
+          if constexpr ((LNF & LN_LAST) != 0) {
+            if (lnlast[itr] >= 0) *reinterpret_cast<float4*>(p.C + (size_t)lnlast[itr] * p.ldc + col) = v;
+          } else {
+            *reinterpret_cast<float4*>(p.C + (size_t)row * p.ldc + col) = v;
+          }
           if constexpr (SCALED) cmax = fmaxf(cmax, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
         }
       }
@@ -231,6 +275,19 @@ __device__ __forceinline__ void epilogue_tile(const P& p, uint32_t tmem_acc, int
       }
     }
     __syncwarp();
+  }
+  if constexpr ((LNF & LN_STATS) != 0) {
+    // the four lanes of a row hold its partial sums over this warp's column chunks: one (sum, sum of squares) pair
+    // per (row, n-tile, column half), added in a fixed order (deterministic)
+    const int nparts = 2 * ((p.N + BN - 1) / BN), part = 2 * (n0 / BN) + half;
+#pragma unroll
+    for (int itr = 0; itr < NIT; ++itr) {
+      float s = st_s[itr], q2 = st_q[itr];
+      s += __shfl_xor_sync(0xffffffffu, s, 1); q2 += __shfl_xor_sync(0xffffffffu, q2, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2); q2 += __shfl_xor_sync(0xffffffffu, q2, 2);
+      const int row = rbase + RPI * itr;
+      if ((lane % LPR) == 0 && row < p.M) p.ln.stats[(size_t)row * nparts + part] = make_float2(s, q2);
+    }
   }
 }
 

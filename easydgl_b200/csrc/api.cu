@@ -94,11 +94,16 @@ struct edgl_handle {
         *logits_ws = nullptr;
   uint8_t *marks = nullptr, *kmask = nullptr;
   long long ws_rows = 0;  // rows of logits_ws
-  // staging for the *_host entry point
-  int64_t* st_ids = nullptr;
-  float* st_ts = nullptr;
-  int32_t* st_idx = nullptr;
-  float* st_val = nullptr;
+  // staging for the *_host entry points: two slots, so the upload of batch i+1 and the download of batch i-1 overlap
+  // the kernels of batch i (copies on two side streams, ordered by events)
+  int64_t* st_ids[2] = {nullptr, nullptr};
+  float* st_ts[2] = {nullptr, nullptr};
+  int32_t* st_idx[2] = {nullptr, nullptr};
+  float* st_val[2] = {nullptr, nullptr};
+  cudaStream_t cs_in = nullptr, cs_out = nullptr;
+  cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
+  bool slot_busy[2] = {false, false}, slot_used[2] = {false, false};
+  int next_slot = 0;
   std::vector<void*> owned;
   // optional per-stage CUDA-event profile
   bool prof_on = false;
@@ -568,11 +573,22 @@ int edgl_create(const edgl_config* cfg, edgl_handle** out) {
     h->ws_rows = r;
     EDGL_ALLOC(h->logits_ws, r * ldw);
   }
-  EDGL_ALLOC(h->st_ids, rows);
-  EDGL_ALLOC(h->st_ts, (long long)cfg->max_batch * h->ts_len);
-  EDGL_ALLOC(h->st_idx, (long long)cfg->max_batch * h->K);
-  EDGL_ALLOC(h->st_val, (long long)cfg->max_batch * h->K);
+  for (int sl = 0; sl < 2; ++sl) {
+    EDGL_ALLOC(h->st_ids[sl], rows);
+    EDGL_ALLOC(h->st_ts[sl], (long long)cfg->max_batch * h->ts_len);
+    EDGL_ALLOC(h->st_idx[sl], (long long)cfg->max_batch * h->K);
+    EDGL_ALLOC(h->st_val[sl], (long long)cfg->max_batch * h->K);
+  }
 #undef EDGL_ALLOC
+  if (!rc) {
+    bool ok = cudaStreamCreateWithFlags(&h->cs_in, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&h->cs_out, cudaStreamNonBlocking) == cudaSuccess;
+    for (int sl = 0; sl < 2 && ok; ++sl)
+      ok = cudaEventCreateWithFlags(&h->ev_h2d[sl], cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&h->ev_done[sl], cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&h->ev_d2h[sl], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) rc = set_error(EDGL_ECUDA, "could not create the copy streams / events of the host entry point");
+  }
   if (rc) {
     edgl_destroy(h);
     return rc;
@@ -585,6 +601,13 @@ int edgl_destroy(edgl_handle* h) {
   if (!h) return 0;
   for (void* p : h->owned) cudaFree(p);
   for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
+  for (int sl = 0; sl < 2; ++sl) {
+    if (h->ev_h2d[sl]) cudaEventDestroy(h->ev_h2d[sl]);
+    if (h->ev_done[sl]) cudaEventDestroy(h->ev_done[sl]);
+    if (h->ev_d2h[sl]) cudaEventDestroy(h->ev_d2h[sl]);
+  }
+  if (h->cs_in) cudaStreamDestroy(h->cs_in);
+  if (h->cs_out) cudaStreamDestroy(h->cs_out);
   delete h;
   return 0;
 }
@@ -824,19 +847,48 @@ int edgl_forward_topk(edgl_handle* h, const int64_t* seqs_i, const float* seqs_t
   return logits_topk(h, h->y, h->d, mask_seen ? seqs_i : nullptr, h->L, h->L, B, idx, val, 0, st);
 }
 
-int edgl_forward_topk_host(edgl_handle* h, const int64_t* seqs_i_host, const float* seqs_t_host, int B,
-                           int mask_seen, int32_t* idx_host, float* val_host, void* stream) {
+int edgl_forward_topk_host_submit(edgl_handle* h, const int64_t* seqs_i_host, const float* seqs_t_host, int B,
+                                  int mask_seen, int32_t* idx_host, float* val_host, void* stream) {
   EDGL_TRY(check_ready(h, B));
   if (!seqs_i_host || !seqs_t_host || !idx_host || !val_host) return set_error(EDGL_EINVAL, "null argument");
-  if (B == 0) return 0;
+  const int sl = h->next_slot;
+  EDGL_REQUIRE(!h->slot_busy[sl], "both staging slots are in flight: call edgl_forward_topk_host_wait first");
+  if (B == 0) return sl;
   cudaStream_t st = (cudaStream_t)stream;
-  EDGL_CUDA(cudaMemcpyAsync(h->st_ids, seqs_i_host, (size_t)B * h->L * sizeof(int64_t), cudaMemcpyHostToDevice, st));
-  EDGL_CUDA(cudaMemcpyAsync(h->st_ts, seqs_t_host, (size_t)B * h->ts_len * sizeof(float), cudaMemcpyHostToDevice, st));
-  EDGL_TRY(edgl_forward_topk(h, h->st_ids, h->st_ts, B, mask_seen, h->st_idx, h->st_val, stream));
-  EDGL_CUDA(cudaMemcpyAsync(idx_host, h->st_idx, (size_t)B * h->K * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-  EDGL_CUDA(cudaMemcpyAsync(val_host, h->st_val, (size_t)B * h->K * sizeof(float), cudaMemcpyDeviceToHost, st));
-  EDGL_CUDA(cudaStreamSynchronize(st));
+  // upload on cs_in (after the kernels that last read this slot's inputs), kernels on the caller's stream, download
+  // on cs_out; pinned host buffers make all three asynchronous
+  if (h->slot_used[sl]) EDGL_CUDA(cudaStreamWaitEvent(h->cs_in, h->ev_done[sl], 0));
+  EDGL_CUDA(cudaMemcpyAsync(h->st_ids[sl], seqs_i_host, (size_t)B * h->L * sizeof(int64_t), cudaMemcpyHostToDevice, h->cs_in));
+  EDGL_CUDA(cudaMemcpyAsync(h->st_ts[sl], seqs_t_host, (size_t)B * h->ts_len * sizeof(float), cudaMemcpyHostToDevice, h->cs_in));
+  EDGL_CUDA(cudaEventRecord(h->ev_h2d[sl], h->cs_in));
+  EDGL_CUDA(cudaStreamWaitEvent(st, h->ev_h2d[sl], 0));
+  if (h->slot_used[sl]) EDGL_CUDA(cudaStreamWaitEvent(st, h->ev_d2h[sl], 0));  // the previous results have left the slot
+  EDGL_TRY(edgl_forward_topk(h, h->st_ids[sl], h->st_ts[sl], B, mask_seen, h->st_idx[sl], h->st_val[sl], stream));
+  EDGL_CUDA(cudaEventRecord(h->ev_done[sl], st));
+  EDGL_CUDA(cudaStreamWaitEvent(h->cs_out, h->ev_done[sl], 0));
+  EDGL_CUDA(cudaMemcpyAsync(idx_host, h->st_idx[sl], (size_t)B * h->K * sizeof(int32_t), cudaMemcpyDeviceToHost, h->cs_out));
+  EDGL_CUDA(cudaMemcpyAsync(val_host, h->st_val[sl], (size_t)B * h->K * sizeof(float), cudaMemcpyDeviceToHost, h->cs_out));
+  EDGL_CUDA(cudaEventRecord(h->ev_d2h[sl], h->cs_out));
+  h->slot_busy[sl] = true;
+  h->slot_used[sl] = true;
+  h->next_slot = sl ^ 1;
+  return sl;
+}
+
+int edgl_forward_topk_host_wait(edgl_handle* h, int slot) {
+  if (!h) return set_error(EDGL_EINVAL, "null handle");
+  EDGL_REQUIRE(slot == 0 || slot == 1, "slot must be 0 or 1");
+  if (!h->slot_busy[slot]) return 0;
+  EDGL_CUDA(cudaEventSynchronize(h->ev_d2h[slot]));
+  h->slot_busy[slot] = false;
   return 0;
+}
+
+int edgl_forward_topk_host(edgl_handle* h, const int64_t* seqs_i_host, const float* seqs_t_host, int B,
+                           int mask_seen, int32_t* idx_host, float* val_host, void* stream) {
+  const int sl = edgl_forward_topk_host_submit(h, seqs_i_host, seqs_t_host, B, mask_seen, idx_host, val_host, stream);
+  if (sl < 0) return sl;
+  return edgl_forward_topk_host_wait(h, sl);
 }
 
 int edgl_logits_topk(edgl_handle* h, const float* y, int64_t y_stride, const int64_t* seen_ids, int seen_len,

@@ -5,6 +5,7 @@
 // Ranking is done on the masked logits: softmax (Base.py:164) is monotone, so the order is the same
 // wherever fp32 softmax is injective (DESIGN.md discusses the underflow corner).
 // Integer/index work: bit-exact by construction (order-preserving uint keys, radix select, ties by index).
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -352,6 +353,129 @@ __device__ void topk_row(const float* __restrict__ p, int vec, int N, int K, int
   write_topk(cand, K, K, col_offset, io, vo);
 }
 
+// ---- short rows (multi-GPU column shards: N of a few thousand, G * B rows): ONE WARP PER ROW, no block barrier.
+// Every lane keeps N / 32 order-preserving keys in registers; the K-th largest key is found by a bit-wise descent
+// (32 counting passes over the registers), ties at the cut are taken in index order with ballots, and the K selected
+// (key, index) pairs are sorted by a 128-element bitonic network that lives in the warp's registers.  Same result,
+// bit for bit, as topk_row: (value desc, index asc).  The CTA-per-row kernel spends ~14 us of barriers and shared-
+// memory sorting per row whatever its length, which is what limited the 8-GPU step (32768 rows of 2251 columns).
+template <int NPL>
+__global__ void __launch_bounds__(256) topk_warp_kernel(const float* __restrict__ logits, int ld, long long rows, int N,
+                                                        int K, int col_offset, long long out_stride,
+                                                        int32_t* __restrict__ idx_out, float* __restrict__ val_out,
+                                                        TopkP2P pp) {
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + w;
+  if (row < rows) {  // warp-uniform
+    const float* p = logits + row * ld;
+    uint32_t k[NPL];
+#pragma unroll
+    for (int j = 0; j < NPL; ++j) {
+      const int i = j * 32 + lane;
+      k[j] = i < N ? f2key(p[i]) : 0u;  // 0 is below the key of every float
+    }
+    const int Keff = K < N ? K : N;
+    uint32_t T = 0;  // becomes the Keff-th largest key: the largest T with #{key >= T} >= Keff
+#pragma unroll 1
+    for (int bit = 31; bit >= 0; --bit) {
+      const uint32_t c = T | (1u << bit);
+      int cnt = 0;
+#pragma unroll
+      for (int j = 0; j < NPL; ++j) cnt += (k[j] >= c) ? 1 : 0;
+      cnt = __reduce_add_sync(0xffffffffu, cnt);
+      if (cnt >= Keff) T = c;
+    }
+    int ngt = 0;
+#pragma unroll
+    for (int j = 0; j < NPL; ++j) ngt += (k[j] > T) ? 1 : 0;
+    ngt = __reduce_add_sync(0xffffffffu, ngt);
+    const int need_eq = Keff - ngt;  // ties at the cut, lowest indices first
+    // the selected pairs, element e of the sort network lives in v[e / 32] of lane e % 32
+    unsigned long long v[4] = {0ull, 0ull, 0ull, 0ull};
+    int base_gt = 0, base_eq = 0;
+    const unsigned int lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int j = 0; j < NPL; ++j) {
+      const int i = j * 32 + lane;
+      const bool gt = k[j] > T, eq = (k[j] == T) && (i < N);
+      const unsigned int bg = __ballot_sync(0xffffffffu, gt), be = __ballot_sync(0xffffffffu, eq);
+      int pos = -1;
+      if (gt) pos = base_gt + __popc(bg & lt);
+      if (eq) {
+        const int pe = base_eq + __popc(be & lt);
+        if (pe < need_eq) pos = ngt + pe;
+      }
+      base_gt += __popc(bg);
+      base_eq += __popc(be);
+      // hand the pair to the lane / register that owns sort slot `pos` (at most 32 selected per j)
+      const unsigned long long mine = compose(k[j], (uint32_t)i);
+      unsigned int sel = __ballot_sync(0xffffffffu, pos >= 0);
+      while (sel) {
+        const int src = __ffs(sel) - 1;
+        sel &= sel - 1;
+        const int ps = __shfl_sync(0xffffffffu, pos, src);
+        const unsigned long long val = __shfl_sync(0xffffffffu, mine, src);
+        if ((ps & 31) == lane) {
+          if ((ps >> 5) == 0) v[0] = val;
+          else if ((ps >> 5) == 1) v[1] = val;
+          else if ((ps >> 5) == 2) v[2] = val;
+          else v[3] = val;
+        }
+      }
+    }
+    // descending bitonic sort of the 128 slots
+#pragma unroll
+    for (int kk = 2; kk <= 128; kk <<= 1) {
+#pragma unroll
+      for (int j = kk >> 1; j > 0; j >>= 1) {
+        if (j >= 32) {
+          const int dm = j >> 5;
+#pragma unroll
+          for (int m = 0; m < 4; ++m) {
+            if ((m & dm) == 0) {
+              const int e = m * 32 + lane;
+              const bool desc = (e & kk) == 0;
+              const unsigned long long a = v[m], b = v[m | dm];
+              const bool sw = desc ? (a < b) : (a > b);
+              v[m] = sw ? b : a;
+              v[m | dm] = sw ? a : b;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int m = 0; m < 4; ++m) v[m] = cmpx64(v[m], m * 32 + lane, kk, j);
+        }
+      }
+    }
+    int32_t* io;
+    float* vo;
+    if (pp.dest) {
+      const long long R = (long long)pp.row_base + row;
+      const int dst = (int)(R / pp.rows_per_dest);
+      io = reinterpret_cast<int32_t*>(pp.dest[dst]) +
+           ((long long)pp.my_rank * pp.rows_per_dest + (R - (long long)dst * pp.rows_per_dest)) * (2 * K);
+      vo = reinterpret_cast<float*>(io + K);
+    } else {
+      io = idx_out + row * out_stride;
+      vo = val_out + row * out_stride;
+    }
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const int e = m * 32 + lane;
+      if (e < K) {
+        if (e < Keff) {
+          io[e] = (int32_t)(0xffffffffu - (uint32_t)(v[m] & 0xffffffffull)) + col_offset;
+          vo[e] = key2f((uint32_t)(v[m] >> 32));
+        } else {
+          io[e] = -1;
+          vo[e] = -INFINITY;
+        }
+      }
+    }
+  }
+  if (pp.dest && pp.signal) p2p_signal_when_grid_done(pp.counter, pp.peer_flags, pp.G, pp.my_rank, pp.epoch);
+}
+
 static int next_pow2(int v) {
   int p = 1;
   while (p < v) p <<= 1;
@@ -367,6 +491,16 @@ int launch_topk(const float* logits, int ld, int B, int N, int K, int col_offset
   EDGL_REQUIRE(K >= 1 && K <= 2048, "topk: K must be in [1,2048] (got %d)", K);
   EDGL_REQUIRE(N >= 1, "topk: N must be >= 1");
   if (B == 0) return 0;
+  // short rows, many of them (column shards of the multi-GPU path): one warp per row
+  static const bool no_warp = getenv("EDGL_TOPK_WARP") != nullptr && getenv("EDGL_TOPK_WARP")[0] == '0';
+  if (!no_warp && K <= 128 && N <= 32 * 96 && B >= 64) {
+    const unsigned grid = (unsigned)((B + 7) / 8);
+    if (N <= 32 * 32) topk_warp_kernel<32><<<grid, 256, 0, st>>>(logits, ld, B, N, K, col_offset, out_stride, idx, val, pp);
+    else if (N <= 32 * 72) topk_warp_kernel<72><<<grid, 256, 0, st>>>(logits, ld, B, N, K, col_offset, out_stride, idx, val, pp);
+    else topk_warp_kernel<96><<<grid, 256, 0, st>>>(logits, ld, B, N, K, col_offset, out_stride, idx, val, pp);
+    EDGL_LAUNCH_CHECK();
+    return 0;
+  }
   const int KP = next_pow2(K);
   const size_t smem = (size_t)(KP > kCandCap ? KP : kCandCap) * 8;
   topk_kernel<<<B, 256, smem, st>>>(logits, ld, N, K, KP, col_offset, out_stride, idx, val, pp);

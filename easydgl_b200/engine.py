@@ -142,6 +142,32 @@ class Engine:
 
     def forward_topk_host(self, seqs_i_cpu, seqs_t_cpu, idx_cpu, val_cpu, mask_seen: bool = True):
         """End-to-end call on HOST buffers (ideally pinned): H2D, forward, top-K, D2H, sync."""
+        self._check_host(seqs_i_cpu, seqs_t_cpu, idx_cpu, val_cpu)
+        B = int(seqs_i_cpu.shape[0])
+        with torch.cuda.device(self.device):
+            check(self.lib.edgl_forward_topk_host(self._handle, seqs_i_cpu.data_ptr(), seqs_t_cpu.data_ptr(), B,
+                                                  int(bool(mask_seen)), idx_cpu.data_ptr(), val_cpu.data_ptr(),
+                                                  _stream()))
+        return idx_cpu, val_cpu
+
+    def forward_topk_host_submit(self, seqs_i_cpu, seqs_t_cpu, idx_cpu, val_cpu, mask_seen: bool = True) -> int:
+        """Asynchronous half of ``forward_topk_host``: enqueue upload, kernels and download of one batch and return
+        its slot (0/1).  Up to two batches may be in flight; the host buffers must stay alive (and, to overlap, be
+        pinned) until ``forward_topk_host_wait(slot)`` returns."""
+        self._check_host(seqs_i_cpu, seqs_t_cpu, idx_cpu, val_cpu)
+        B = int(seqs_i_cpu.shape[0])
+        with torch.cuda.device(self.device):
+            slot = self.lib.edgl_forward_topk_host_submit(self._handle, seqs_i_cpu.data_ptr(), seqs_t_cpu.data_ptr(), B,
+                                                          int(bool(mask_seen)), idx_cpu.data_ptr(), val_cpu.data_ptr(),
+                                                          _stream())
+        if slot < 0:
+            check(slot)
+        return slot
+
+    def forward_topk_host_wait(self, slot: int):
+        check(self.lib.edgl_forward_topk_host_wait(self._handle, int(slot)))
+
+    def _check_host(self, seqs_i_cpu, seqs_t_cpu, idx_cpu, val_cpu):
         B = int(seqs_i_cpu.shape[0])
         for t in (seqs_i_cpu, seqs_t_cpu, idx_cpu, val_cpu):
             if t.device.type != "cpu" or not t.is_contiguous():
@@ -154,11 +180,6 @@ class Engine:
             raise ValueError("bad input shapes")
         if idx_cpu.numel() < B * self.K or val_cpu.numel() < B * self.K:
             raise ValueError("output buffers too small")
-        with torch.cuda.device(self.device):
-            check(self.lib.edgl_forward_topk_host(self._handle, seqs_i_cpu.data_ptr(), seqs_t_cpu.data_ptr(), B,
-                                                  int(bool(mask_seen)), idx_cpu.data_ptr(), val_cpu.data_ptr(),
-                                                  _stream()))
-        return idx_cpu, val_cpu
 
     def encode(self, seqs_i, seqs_t) -> torch.Tensor:
         seqs_i, seqs_t, B = self._inputs(seqs_i, seqs_t)

@@ -115,6 +115,15 @@ int edgl_forward_topk(edgl_handle* h, const int64_t* seqs_i, const float* seqs_t
  * stream synchronised on return.  This is the end-to-end call bench.py times as "e2e". */
 int edgl_forward_topk_host(edgl_handle* h, const int64_t* seqs_i_host, const float* seqs_t_host, int B,
                            int mask_seen, int32_t* idx_host, float* val_host, void* stream);
+/* The same call split in two, so that a caller that feeds batch after batch (the reference's eval loop,
+ * main.py:133-143, one sess.run per batch) keeps TWO batches in flight: submit enqueues upload (side stream),
+ * kernels (`stream`) and download (second side stream) of one batch and returns its staging slot (0 or 1, or a
+ * negative error code) without waiting; wait blocks until that slot's idx/val have arrived in the host buffers.
+ * With pinned host buffers the upload of batch i+1 and the download of batch i-1 overlap the kernels of batch i.
+ * At most two submits may be outstanding. */
+int edgl_forward_topk_host_submit(edgl_handle* h, const int64_t* seqs_i_host, const float* seqs_t_host, int B,
+                                  int mask_seen, int32_t* idx_host, float* val_host, void* stream);
+int edgl_forward_topk_host_wait(edgl_handle* h, int slot);
 
 /* ---- the two halves of the forward, for the column-sharded multi-GPU path ---- */
 /* Encoder up to y = hidden[:, -1]  [B,d]  (EasyDGL.py:69-146 / CTSMA.py:46-87). */

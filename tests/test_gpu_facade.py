@@ -153,3 +153,41 @@ def test_restore_from_saver_checkpoint_and_mark_pkl(tmp_path, name):
     again = ranking(flags, device=DEV)
     again.restore(str(tmp_path / "ckpt"))                                    # directory with a `checkpoint` file
     assert torch.equal(again(features, False).cpu(), want)
+
+
+def test_host_entry_point_submit_wait_pipeline():
+    """edgl_forward_topk_host_submit / _wait: four batches through the two staging slots give the results of the
+    synchronous device-resident call, in order, and a third outstanding submit is refused."""
+    from easydgl_b200 import synth
+    from easydgl_b200.engine import Engine
+    cfg = synth.make_config(model="EasyDGL", num_units=64, seqslen=30, num_items=500, num_heads=4, num_blocks=1,
+                            num_events=16)
+    W = synth.make_weights(cfg, mode="parity")
+    B = 16
+    eng = Engine(cfg, W, max_batch=B, device=DEV)
+    batches = [synth.make_inputs(cfg, B, seed=77 + i) for i in range(4)]
+    ref = [eng.forward_topk(b["seqs_i"].to(DEV), b["seqs_t"].to(DEV), True) for b in batches]
+    ins = [(b["seqs_i"].pin_memory(), b["seqs_t"].pin_memory()) for b in batches]
+    outs = [(torch.empty((B, eng.K), dtype=torch.int32).pin_memory(), torch.empty((B, eng.K)).pin_memory())
+            for _ in batches]
+    prev = None
+    for i in range(4):
+        slot = eng.forward_topk_host_submit(ins[i][0], ins[i][1], outs[i][0], outs[i][1], True)
+        assert slot == i % 2
+        if prev is not None:
+            eng.forward_topk_host_wait(prev)
+        prev = slot
+    eng.forward_topk_host_wait(prev)
+    for i in range(4):
+        assert torch.equal(outs[i][0], ref[i][0].cpu()) and torch.equal(outs[i][1], ref[i][1].cpu()), i
+    # two outstanding submits are the limit
+    s0 = eng.forward_topk_host_submit(ins[0][0], ins[0][1], outs[0][0], outs[0][1], True)
+    s1 = eng.forward_topk_host_submit(ins[1][0], ins[1][1], outs[1][0], outs[1][1], True)
+    with pytest.raises(ValueError):
+        eng.forward_topk_host_submit(ins[2][0], ins[2][1], outs[2][0], outs[2][1], True)
+    eng.forward_topk_host_wait(s0)
+    eng.forward_topk_host_wait(s1)
+    # the synchronous call still works
+    i2, v2 = eng.forward_topk_host(ins[2][0], ins[2][1], outs[2][0], outs[2][1], True)
+    assert torch.equal(i2, ref[2][0].cpu())
+    eng.close()

@@ -244,6 +244,35 @@ def test_topk_ties_and_masking():
     assert torch.isinf(lg.cpu()[5, seen[5]]).all()
 
 
+@pytest.mark.parametrize("N,K", [(31, 100), (1000, 100), (2251, 100), (3072, 100), (2251, 7), (1500, 128)])
+def test_topk_short_rows_warp_kernel(N, K):
+    """The one-warp-per-row kernel that serves the column shards of the multi-GPU path (many rows of a few thousand
+    columns): bit-identical to tf.nn.top_k semantics, including ties at the cut, -inf and rows shorter than K."""
+    from easydgl_b200 import engine
+    g = torch.Generator().manual_seed(60 + N + K)
+    B = 300
+    logits = torch.randn(B, N, generator=g)
+    logits[0] = 0.5                                             # all tied -> indices 0..K-1
+    logits[1, :] = torch.round(logits[1] * 2) / 2               # heavy ties, also at the cut
+    logits[2, N // 10:N // 2] = float("-inf")                   # many masked
+    logits[3, :] = float("-inf")                                # everything masked
+    logits[4, min(5, N - 1)] = float("inf")
+    logits[5, :] = torch.round(logits[5])                       # a handful of distinct values
+    logits[6, ::2] = -0.0
+    logits[6, 1::2] = 0.0                                       # -0.0 < +0.0 in the key order (DESIGN.md)
+    seen = torch.randint(0, N, (B, 17), generator=g)
+    ref_v, ref_i = O.eval_topk(logits.double(), seen, True, min(K, N), rank_on="logits")
+    idx, val = engine.topk(logits.clone().to(DEV), K, seen.to(DEV))
+    idx, val = idx.cpu().long(), val.cpu().double()
+    rows = [r for r in range(B) if r != 6]                       # row 6: signed zeros are ordered by sign bit here
+    assert torch.equal(idx[rows, :min(K, N)], ref_i[rows]), "top-K indices must be bit-identical"
+    assert torch.equal(val[rows, :min(K, N)], ref_v[rows])
+    if N < K:
+        assert bool((idx[:, N:] == -1).all()) and bool(torch.isinf(val[:, N:]).all())
+    if N >= 1000:
+        assert bool((val[6, :K] == 0).all()) and bool((idx[6, :K] % 2 == 1).all())
+
+
 def test_topk_small_n_pads():
     from easydgl_b200 import engine
     logits = torch.tensor([[0.1, 0.7, -0.2]], device=DEV)

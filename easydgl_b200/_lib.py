@@ -46,6 +46,7 @@ _SIGS = {
     "edgl_forward_topk_host_submit": (_I, [_P, _P, _P, _I, _I, _P, _P, _P]),
     "edgl_forward_topk_host_wait": (_I, [_P, _I]),
     "edgl_encode": (_I, [_P, _P, _P, _I, _P, _P]),
+    "edgl_encode_packed": (_I, [_P, _P, _P, _I, _P, C.c_int64, _P]),
     "edgl_logits_topk": (_I, [_P, _P, C.c_int64, _P, _I, C.c_int64, _I, C.c_int64, _P, _P, _P]),
     "edgl_xchg_alloc": (_I, [C.c_int64, C.POINTER(_P), _P]),
     "edgl_xchg_open": (_I, [_P, C.POINTER(_P)]),

@@ -257,7 +257,7 @@ EmbedArgs embed_args(const edgl_handle* h, const int64_t* ids, const float* ts, 
 }
 
 // EasyDGL.__call__ up to y = hidden[:, -1]  (EasyDGL.py:69-146)
-int encode_easydgl(edgl_handle* h, const int64_t* ids, const float* ts, int B, float* y, cudaStream_t st) {
+int encode_easydgl(edgl_handle* h, const int64_t* ids, const float* ts, int B, float* y, long long ldy, cudaStream_t st) {
   const int d = h->d, L = h->L;
   const long long rows = (long long)B * L;
   EmbedArgs e = embed_args(h, ids, ts, B);
@@ -332,7 +332,7 @@ int encode_easydgl(edgl_handle* h, const int64_t* ids, const float* ts, int B, f
                           true, nullptr, nullptr, nullptr, &e_tr));
         mark(h, ST_LN_OUT, st);
         EDGL_TRY(launch_ln_finalize(h->ln_parts, np, B, L, d, h->ln_rs3, h->tr_last, F(h->mt, "tr_ln_g"), F(h->mt, "tr_ln_b"),
-                                    y, (f16 && y == h->y) ? am + AMAX_Y : nullptr, st));
+                                    y, (f16 && y == h->y) ? am + AMAX_Y : nullptr, st, ldy));
         mark(h, ST_END, st);
         return 0;
       }
@@ -366,13 +366,13 @@ int encode_easydgl(edgl_handle* h, const int64_t* ids, const float* ts, int B, f
                     (f16 && (h->f16_mask & 16)) ? h->mt16.at("tr_w") : nullptr, am + AMAX_LN2));  // :138
   mark(h, ST_LN_OUT, st);
   EDGL_TRY(launch_layernorm(h->p0, F(h->mt, "tr_ln_g"), F(h->mt, "tr_ln_b"), B, L, d, y, true, st,
-                            (f16 && y == h->y) ? am + AMAX_Y : nullptr));                 // :139,146
+                            (f16 && y == h->y) ? am + AMAX_Y : nullptr, ldy));            // :139,146
   mark(h, ST_END, st);
   return 0;
 }
 
 // CTSMA.__call__ up to y (CTSMA.py:46-87)
-int encode_ctsma(edgl_handle* h, const int64_t* ids, const float* ts, int B, float* y, cudaStream_t st) {
+int encode_ctsma(edgl_handle* h, const int64_t* ids, const float* ts, int B, float* y, long long ldy, cudaStream_t st) {
   const int d = h->d, L = h->L;
   const long long rows = (long long)B * L;
   EmbedArgs e = embed_args(h, ids, ts, B);
@@ -403,14 +403,16 @@ int encode_ctsma(edgl_handle* h, const int64_t* ids, const float* ts, int B, flo
     cin = d;
   }
   mark(h, ST_LN_OUT, st);
-  EDGL_TRY(launch_layernorm(cur, F(h->mt, "out_ln_g"), F(h->mt, "out_ln_b"), B, L, d, y, true, st));  // CTSMA.py:80,87
+  EDGL_TRY(launch_layernorm(cur, F(h->mt, "out_ln_g"), F(h->mt, "out_ln_b"), B, L, d, y, true, st, nullptr, ldy));  // CTSMA.py:80,87
   mark(h, ST_END, st);
   return 0;
 }
 
-int encode(edgl_handle* h, const int64_t* ids, const float* ts, int B, float* y, cudaStream_t st) {
+int encode(edgl_handle* h, const int64_t* ids, const float* ts, int B, float* y, cudaStream_t st, long long ldy = 0) {
   if (B == 0) return 0;
-  return h->cfg.model == EDGL_MODEL_EASYDGL ? encode_easydgl(h, ids, ts, B, y, st) : encode_ctsma(h, ids, ts, B, y, st);
+  if (ldy == 0) ldy = h->d;
+  return h->cfg.model == EDGL_MODEL_EASYDGL ? encode_easydgl(h, ids, ts, B, y, ldy, st)
+                                            : encode_ctsma(h, ids, ts, B, y, ldy, st);
 }
 
 // logits[r0:r0+rc, c0:c1] = y @ table[c0:c1]^T + bias   (EasyDGL.py:149-150 / CTSMA.py:89-90, Base.py:106-110)
@@ -820,6 +822,19 @@ int edgl_encode(edgl_handle* h, const int64_t* seqs_i, const float* seqs_t, int 
   EDGL_TRY(check_ready(h, B));
   if (!seqs_i || !seqs_t || !y) return set_error(EDGL_EINVAL, "null argument");
   return encode(h, seqs_i, seqs_t, B, y, (cudaStream_t)stream);
+}
+
+int edgl_encode_packed(edgl_handle* h, const int64_t* seqs_i, const float* seqs_t, int B, float* rows, int64_t row_stride,
+                       void* stream) {
+  EDGL_TRY(check_ready(h, B));
+  if (!seqs_i || !seqs_t || !rows) return set_error(EDGL_EINVAL, "null argument");
+  EDGL_REQUIRE(row_stride >= h->d + 2 * h->L && row_stride % 4 == 0, "row_stride must be a multiple of 4 >= d + 2 L");
+  cudaStream_t st = (cudaStream_t)stream;
+  EDGL_TRY(encode(h, seqs_i, seqs_t, B, rows, st, row_stride));
+  // the ids ride behind y in the same row (raw bytes in fp32 lanes): one strided device-to-device copy
+  EDGL_CUDA(cudaMemcpy2DAsync(rows + h->d, (size_t)row_stride * sizeof(float), seqs_i, (size_t)h->L * sizeof(int64_t),
+                              (size_t)h->L * sizeof(int64_t), (size_t)B, cudaMemcpyDeviceToDevice, st));
+  return 0;
 }
 
 int edgl_forward_logits(edgl_handle* h, const int64_t* seqs_i, const float* seqs_t, int B, float* logits,

@@ -82,7 +82,8 @@ int ln_stats_parts(int N);  // number of partials per row the tensor-core GEMM w
 // (mean, rstd)[b] from the row partials of B sequences of L rows x C columns; optionally y[b] = LN(x_last[b]) with
 // x_last [B, C] (the stored last rows), gamma, beta
 int launch_ln_finalize(const float2* parts, int nparts, int B, int L, int C, float2* rs, const float* x_last,
-                       const float* gamma, const float* beta, float* y, unsigned int* y_amax, cudaStream_t st);
+                       const float* gamma, const float* beta, float* y, unsigned int* y_amax, cudaStream_t st,
+                       long long y_stride = 0);
 // C[M,N] (ldc) = act(A[M,K] (lda) @ W + bias[N] + pbias[(m % pperiod), N]) + R[M,N] (ldr)
 // W is [K,N] (ldw) row-major, or, if w_is_nk, [N,K] (ldw) row-major (C = A @ W^T).
 // col0_const: if non-null-flag set, global column (col_offset+0)==0 gets exactly bias (acc ignored)
@@ -182,7 +183,7 @@ int launch_intensity(const float* H, const float* spans, const uint8_t* marks, c
 
 // LayerNorm over (L,C) jointly per sample. last_only: write only row L-1 to out [B,C].
 int launch_layernorm(const float* x, const float* gamma, const float* beta, int B, int L, int C, float* out,
-                     bool last_only, cudaStream_t st, unsigned int* out_amax = nullptr);
+                     bool last_only, cudaStream_t st, unsigned int* out_amax = nullptr, long long out_stride = 0);
 
 int launch_mask_seen(float* logits, int ld, int B, const int64_t* ids, int seen_len, long long seen_stride,
                      long long col0, long long col1, cudaStream_t st);

@@ -25,7 +25,7 @@ template <bool CACHE>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, int L, int C,
                                                         float* __restrict__ out, int last_only,
-                                                        unsigned int* __restrict__ out_amax) {
+                                                        unsigned int* __restrict__ out_amax, long long out_stride) {
   extern __shared__ __align__(16) float xs[];
   __shared__ float red[8];
   const long long n = (long long)L * C;
@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   float omax = 0.f;  // max |out| over what this thread writes
   if (last_only) {
     const float* src = (CACHE ? xs : xp) + (long long)(L - 1) * C;
-    float* op = out + (long long)blockIdx.x * C;
+    float* op = out + (long long)blockIdx.x * out_stride;
     for (int c = threadIdx.x; c < C; c += 256) {
       const float inv = rstd * gamma[c];
       const float o = src[c] * inv + (beta[c] - mean * inv);
@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(256) ln_finalize_kernel(const float2* __restri
                                                           const float* __restrict__ x_last,
                                                           const float* __restrict__ gamma,
                                                           const float* __restrict__ beta, float* __restrict__ y,
-                                                          unsigned int* __restrict__ y_amax) {
+                                                          unsigned int* __restrict__ y_amax, long long y_stride) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= B) return;
   const float2* p = parts + (size_t)warp * L * nparts;
@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(256) ln_finalize_kernel(const float2* __restri
     for (int c = lane; c < C; c += 32) {
       const float inv = rstd * gamma[c];
       const float o = x_last[(size_t)warp * C + c] * inv + (beta[c] - meanf * inv);
-      y[(size_t)warp * C + c] = o;
+      y[(size_t)warp * y_stride + c] = o;
       omax = fmaxf(omax, fabsf(o));
     }
     if (y_amax) amax_publish(y_amax, omax, lane);
@@ -122,16 +122,19 @@ __global__ void __launch_bounds__(256) ln_finalize_kernel(const float2* __restri
 }
 
 int launch_ln_finalize(const float2* parts, int nparts, int B, int L, int C, float2* rs, const float* x_last,
-                       const float* gamma, const float* beta, float* y, unsigned int* y_amax, cudaStream_t st) {
+                       const float* gamma, const float* beta, float* y, unsigned int* y_amax, cudaStream_t st,
+                       long long y_stride) {
   if (B == 0) return 0;
+  if (y_stride == 0) y_stride = C;
   ln_finalize_kernel<<<cdiv((long long)B * 32, 256), 256, 0, st>>>(parts, nparts, B, L, C, rs, x_last, gamma, beta, y,
-                                                                     y_amax);
+                                                                     y_amax, y_stride);
   EDGL_LAUNCH_CHECK();
   return 0;
 }
 
 int launch_layernorm(const float* x, const float* gamma, const float* beta, int B, int L, int C, float* out,
-                     bool last_only, cudaStream_t st, unsigned int* out_amax) {
+                     bool last_only, cudaStream_t st, unsigned int* out_amax, long long out_stride) {
+  if (out_stride == 0) out_stride = C;
   EDGL_REQUIRE(C % 4 == 0, "layernorm: channel count must be a multiple of 4 (got %d)", C);
   EDGL_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
                    (reinterpret_cast<uintptr_t>(gamma) & 15) == 0 && (reinterpret_cast<uintptr_t>(beta) & 15) == 0,
@@ -141,9 +144,9 @@ int launch_layernorm(const float* x, const float* gamma, const float* beta, int 
   if (bytes <= 200 * 1024) {
     auto kern = layernorm_kernel<true>;
     EDGL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    kern<<<B, 256, bytes, st>>>(x, gamma, beta, L, C, out, last_only ? 1 : 0, out_amax);
+    kern<<<B, 256, bytes, st>>>(x, gamma, beta, L, C, out, last_only ? 1 : 0, out_amax, out_stride);
   } else {
-    layernorm_kernel<false><<<B, 256, 0, st>>>(x, gamma, beta, L, C, out, last_only ? 1 : 0, out_amax);
+    layernorm_kernel<false><<<B, 256, 0, st>>>(x, gamma, beta, L, C, out, last_only ? 1 : 0, out_amax, out_stride);
   }
   EDGL_LAUNCH_CHECK();
   return 0;

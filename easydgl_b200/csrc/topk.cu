@@ -491,9 +491,13 @@ int launch_topk(const float* logits, int ld, int B, int N, int K, int col_offset
   EDGL_REQUIRE(K >= 1 && K <= 2048, "topk: K must be in [1,2048] (got %d)", K);
   EDGL_REQUIRE(N >= 1, "topk: N must be >= 1");
   if (B == 0) return 0;
-  // short rows, many of them (column shards of the multi-GPU path): one warp per row
-  static const bool no_warp = getenv("EDGL_TOPK_WARP") != nullptr && getenv("EDGL_TOPK_WARP")[0] == '0';
-  if (!no_warp && K <= 128 && N <= 32 * 96 && B >= 64) {
+  // short rows, many of them (column shards of the multi-GPU path): one warp per row.  Opt-in (EDGL_TOPK_WARP=1,
+  // read per call): bit-identical, but measured SLOWER than the CTA kernel at the shape it was written for (8 GPUs,
+  // 32768 rows x 2251 columns: 0.65 ms vs 0.39 ms) - the 32 counting passes over 72 registers cost ~7 K
+  // instructions per row.
+  const char* we = getenv("EDGL_TOPK_WARP");
+  const bool use_warp = we != nullptr && we[0] == '1';
+  if (use_warp && K <= 128 && N <= 32 * 96 && B >= 64) {
     const unsigned grid = (unsigned)((B + 7) / 8);
     if (N <= 32 * 32) topk_warp_kernel<32><<<grid, 256, 0, st>>>(logits, ld, B, N, K, col_offset, out_stride, idx, val, pp);
     else if (N <= 32 * 72) topk_warp_kernel<72><<<grid, 256, 0, st>>>(logits, ld, B, N, K, col_offset, out_stride, idx, val, pp);
@@ -539,6 +543,70 @@ __global__ void __launch_bounds__(256) topk_merge_kernel(const float* __restrict
   }
 }
 
+// Merge of per-shard lists that are already SORTED (value desc, index asc; padding last) - what edgl_logits_topk
+// writes: every candidate's final position is its position in its own list plus, for every other list, the number
+// of entries that beat it (a binary search), so no sort is needed.  Unsorted input (block-uniform check) takes the
+// bitonic path of topk_merge_kernel.  4096 rows x 8 shards: 0.215 ms (sort of 1024 entries per row) -> see DESIGN.md.
+__global__ void __launch_bounds__(256) topk_merge_rank_kernel(const float* __restrict__ cv, const int32_t* __restrict__ ci,
+                                                              int G, int Bt, int K, int KP, long long shard_stride,
+                                                              long long row_stride, int32_t* __restrict__ idx_out,
+                                                              float* __restrict__ val_out) {
+  extern __shared__ __align__(16) unsigned long long cand[];  // [KP] >= G * K
+  const int row = blockIdx.x, n = G * K;
+  int bad = 0;
+  for (int i = threadIdx.x; i < KP; i += 256) {
+    unsigned long long c = 0ull;
+    if (i < n) {
+      const int g = i / K, j = i - g * K;
+      const long long o = (long long)g * shard_stride + (long long)row * row_stride + j;
+      const int32_t id = ci[o];
+      if (id >= 0) c = compose(f2key(cv[o]), (uint32_t)id);
+    }
+    cand[i] = c;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += 256) {
+    const int j = i % K;
+    if (j + 1 < K && cand[i] < cand[i + 1]) bad = 1;
+  }
+  if (__syncthreads_or(bad)) {  // not sorted: exact general path
+    bitonic_desc(cand, KP);
+    for (int i = threadIdx.x; i < K; i += 256) {
+      const unsigned long long c = cand[i];
+      const long long o = (long long)row * K + i;
+      idx_out[o] = c != 0ull ? (int32_t)(0xffffffffu - (uint32_t)(c & 0xffffffffull)) : -1;
+      val_out[o] = c != 0ull ? key2f((uint32_t)(c >> 32)) : -INFINITY;
+    }
+    return;
+  }
+  for (int i = threadIdx.x; i < K; i += 256) {  // padding first; real entries overwrite it after the barrier
+    idx_out[(long long)row * K + i] = -1;
+    val_out[(long long)row * K + i] = -INFINITY;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += 256) {
+    const unsigned long long c = cand[i];
+    if (c == 0ull) continue;
+    const int g = i / K;
+    int rank = i - g * K;
+    for (int g2 = 0; g2 < G; ++g2) {
+      if (g2 == g) continue;
+      const unsigned long long* lst = cand + g2 * K;
+      int lo = 0, hi = K;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (lst[mid] > c) lo = mid + 1; else hi = mid;
+      }
+      rank += lo;
+      if (rank >= K) break;
+    }
+    if (rank < K) {
+      idx_out[(long long)row * K + rank] = (int32_t)(0xffffffffu - (uint32_t)(c & 0xffffffffull));
+      val_out[(long long)row * K + rank] = key2f((uint32_t)(c >> 32));
+    }
+  }
+}
+
 int launch_topk_merge(const float* cand_val, const int32_t* cand_idx, int G, int Bt, int K, long long shard_stride,
                       long long row_stride, int32_t* idx, float* val, cudaStream_t st) {
   if (row_stride == 0) row_stride = K;
@@ -546,7 +614,8 @@ int launch_topk_merge(const float* cand_val, const int32_t* cand_idx, int G, int
   EDGL_REQUIRE(G >= 1 && K >= 1 && (long long)G * K <= 16384, "topk_merge: G*K must be <= 16384");
   if (Bt == 0) return 0;
   const int KP = next_pow2(G * K);
-  auto kern = topk_merge_kernel;
+  static const bool old_merge = getenv("EDGL_MERGE_SORT") != nullptr;
+  auto kern = old_merge ? topk_merge_kernel : topk_merge_rank_kernel;
   const size_t smem = (size_t)KP * 8;
   if (smem > 48 * 1024) EDGL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<Bt, 256, smem, st>>>(cand_val, cand_idx, G, Bt, K, KP, shard_stride, row_stride, idx, val);

@@ -188,6 +188,18 @@ class Engine:
             check(self.lib.edgl_encode(self._handle, seqs_i.data_ptr(), seqs_t.data_ptr(), B, y.data_ptr(), _stream()))
         return y
 
+    def encode_packed(self, seqs_i, seqs_t, rows: torch.Tensor) -> torch.Tensor:
+        """Encoder output written straight into the packed exchange rows ``rows`` [B, >= d + 2L] fp32:
+        ``[y | seqs_i as raw bytes]`` per row (the all-gather message of the multi-GPU path)."""
+        seqs_i, seqs_t, B = self._inputs(seqs_i, seqs_t)
+        if rows.dtype != torch.float32 or rows.device != self.device or rows.dim() != 2 or rows.stride(1) != 1 \
+                or rows.shape[0] < B:
+            raise ValueError("rows must be a 2-D fp32 tensor on %s with at least B rows" % self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.edgl_encode_packed(self._handle, seqs_i.data_ptr(), seqs_t.data_ptr(), B, rows.data_ptr(),
+                                              int(rows.stride(0)), _stream()))
+        return rows
+
     def logits_topk(self, y, seen_ids=None, out=None, out_stride=0):
         """Local top-K of this handle's item shard for rows ``y`` [Bt,d]; global column ids.
         ``y`` / ``seen_ids`` may be row-strided views (e.g. columns of the packed exchange buffer);
@@ -272,11 +284,18 @@ def topk_merge(cand_val: torch.Tensor, cand_idx: torch.Tensor):
     return topk_merge_raw(cand_val.data_ptr(), cand_idx.data_ptr(), G, Bt, K, 0, 0, cand_val.device)
 
 
-def topk_merge_raw(val_ptr: int, idx_ptr: int, G: int, Bt: int, K: int, shard_stride: int, row_stride: int, device):
-    """Merge with explicit base pointers / strides (used on the packed exchange buffer)."""
+def topk_merge_raw(val_ptr: int, idx_ptr: int, G: int, Bt: int, K: int, shard_stride: int, row_stride: int, device,
+                   out=None):
+    """Merge with explicit base pointers / strides (used on the packed exchange buffer).  ``out=(idx, val)``:
+    contiguous [Bt, K] int32 / fp32 tensors to write into."""
     lib = _lib.load()
-    idx = torch.empty((Bt, K), dtype=torch.int32, device=device)
-    val = torch.empty((Bt, K), dtype=torch.float32, device=device)
+    if out is None:
+        idx = torch.empty((Bt, K), dtype=torch.int32, device=device)
+        val = torch.empty((Bt, K), dtype=torch.float32, device=device)
+    else:
+        idx, val = out
+        if not (idx.is_contiguous() and val.is_contiguous()):
+            raise ValueError("merge outputs must be contiguous")
     with torch.cuda.device(device):
         check(lib.edgl_topk_merge(val_ptr, idx_ptr, G, Bt, K, shard_stride, row_stride, idx.data_ptr(), val.data_ptr(),
                                   _stream()))

@@ -128,6 +128,11 @@ int edgl_forward_topk_host_wait(edgl_handle* h, int slot);
 /* ---- the two halves of the forward, for the column-sharded multi-GPU path ---- */
 /* Encoder up to y = hidden[:, -1]  [B,d]  (EasyDGL.py:69-146 / CTSMA.py:46-87). */
 int edgl_encode(edgl_handle* h, const int64_t* seqs_i, const float* seqs_t, int B, float* y, void* stream);
+/* The encoder writing straight into the packed exchange rows of the multi-GPU path: row b of `rows` (row_stride
+ * floats apart, >= d + 2 L) receives [y (d fp32) | seqs_i[b] (L int64, raw bytes)] - the message every rank
+ * all-gathers, with no packing pass in between. */
+int edgl_encode_packed(edgl_handle* h, const int64_t* seqs_i, const float* seqs_t, int B, float* rows, int64_t row_stride,
+                       void* stream);
 /* y [Bt,d] x this handle's item-table shard -> logits + bias (EasyDGL.py:149-150), optional seen-mask
  * with seen_ids int64 [Bt,seen_len] (may be NULL), local top-K with GLOBAL column ids.
  * Strides are in elements, 0 = dense: row r of y starts at y[r*y_stride] (multiple of 4), of seen_ids at

@@ -245,10 +245,13 @@ def test_topk_ties_and_masking():
 
 
 @pytest.mark.parametrize("N,K", [(31, 100), (1000, 100), (2251, 100), (3072, 100), (2251, 7), (1500, 128)])
-def test_topk_short_rows_warp_kernel(N, K):
-    """The one-warp-per-row kernel that serves the column shards of the multi-GPU path (many rows of a few thousand
-    columns): bit-identical to tf.nn.top_k semantics, including ties at the cut, -inf and rows shorter than K."""
+@pytest.mark.parametrize("warp", ["1", "0"])
+def test_topk_short_rows_warp_kernel(N, K, warp, monkeypatch):
+    """Many short rows (the column shards of the multi-GPU path) through the one-warp-per-row kernel (EDGL_TOPK_WARP=1,
+    opt-in) and the default CTA-per-row kernel: bit-identical to tf.nn.top_k semantics, including ties at the cut,
+    -inf and rows shorter than K."""
     from easydgl_b200 import engine
+    monkeypatch.setenv("EDGL_TOPK_WARP", warp)
     g = torch.Generator().manual_seed(60 + N + K)
     B = 300
     logits = torch.randn(B, N, generator=g)
@@ -298,3 +301,22 @@ def test_topk_merge_equals_global(G):
         cv.append(v)
     mi, mv = engine.topk_merge(torch.stack(cv), torch.stack(ci))
     assert torch.equal(mi, gi) and torch.equal(mv, gv)
+    # lists that are NOT sorted (the kernel's general path) and lists with padding give the same answer
+    perm = torch.randperm(K, generator=g)
+    mi2, mv2 = engine.topk_merge(torch.stack(cv)[:, :, perm].contiguous(), torch.stack(ci)[:, :, perm].contiguous())
+    assert torch.equal(mi2, gi) and torch.equal(mv2, gv)
+    cvp, cip = torch.stack(cv).clone(), torch.stack(ci).clone()
+    cvp[:, :, K // 2:] = float("-inf")
+    cip[:, :, K // 2:] = -1
+    mi3, mv3 = engine.topk_merge(cvp, cip)
+    half = torch.cat([c[:, :K // 2] for c in cv], 1).cpu()
+    hidx = torch.cat([c[:, :K // 2] for c in ci], 1).cpu()
+    rv, ri = O.topk_lower_index_first(half.double(), min(K, half.shape[1]))
+    # reference: sort the G*K/2 surviving candidates by (value desc, global index asc)
+    order = torch.argsort(hidx, dim=1, stable=True)
+    hv, hi = torch.gather(half, 1, order), torch.gather(hidx, 1, order)
+    o2 = torch.argsort(-hv.double(), dim=1, stable=True)[:, :K]
+    want_i, want_v = torch.gather(hi, 1, o2), torch.gather(hv, 1, o2)
+    n_valid = want_i.shape[1]
+    assert torch.equal(mi3.cpu()[:, :n_valid], want_i.to(torch.int32)) and torch.equal(mv3.cpu()[:, :n_valid], want_v)
+    assert bool((mi3.cpu()[:, n_valid:] == -1).all())

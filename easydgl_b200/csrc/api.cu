@@ -543,7 +543,7 @@ int edgl_create(const edgl_config* cfg, edgl_handle** out) {
     // LayerNorm folded into the tensor-core dense layers: EasyDGL, d a multiple of 16, tensor-core GEMMs in use
     const char* ge = getenv("EDGL_GEMM");
     const char* le = getenv("EDGL_LN_FUSE");
-    h->ln_fuse = easy && d % 16 == 0 && !(ge && ge[0] == 's') && !(le && le[0] == '0');
+    h->ln_fuse = easy && d % 16 == 0 && d <= 256 && !(ge && ge[0] == 's') && !(le && le[0] == '0');
     if (h->ln_fuse) {
       EDGL_ALLOC(h->ln_parts, rows * ln_stats_parts(d));
       EDGL_ALLOC(h->ln_rs1, cfg->max_batch);

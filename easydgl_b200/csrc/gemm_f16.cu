@@ -27,7 +27,7 @@ namespace tcf {
 using namespace tcc;
 
 // BK (tc_common.cuh) = 32 elements per k-block: one 128-byte swizzle row of fp32 A, one 64-byte row of fp16
-constexpr int NTHREADS = 512;
+constexpr int NTHREADS = TC_THREADS;
 
 // K-major, 64B-swizzled shared-memory operand descriptor (rows of 64 B = 32 halves, 8-row atoms 512 B apart)
 __device__ __forceinline__ uint64_t umma_desc64(uint32_t saddr) {
@@ -97,7 +97,7 @@ struct Smem {
   static constexpr int B_BYTES = BN * BK * 2;     // fp16 W hi (and lo) tile (SW64)
   static constexpr int STAGE = A32_BYTES + 2 * AH_BYTES + 2 * B_BYTES;
   static constexpr int STAGES = (BN == 256) ? 3 : 4;
-  static constexpr int BYTES = STAGES * STAGE + 1024 /*align*/ + 256 /*barriers*/ + 8 * 32 * CP * 4 /*epilogue*/;
+  static constexpr int BYTES = STAGES * STAGE + 1024 /*align*/ + 256 /*barriers*/ + EPI_WARPS * 32 * CP * 4 /*epilogue*/;
 };
 
 template <int BN, int ACT>
@@ -131,7 +131,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 256);
+      mbar_init(&tempty[i], EPI_WARPS * 32);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -202,11 +202,11 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         umma_commit(&tfull[acc]);          // accumulator complete
       }
     }
-  } else if (warp >= 12) {
+  } else if (warp >= SPLIT_WARP0) {
     // ------------------------------------------------------------------ splitters: fp32 (SW128) -> fp16 hi, lo (SW64)
     // thread = tile row.  Source row r: 128 B at (r/8)*1024 + (r%8)*128, 16-byte chunk c stored at c ^ (r%8).
     // Destination row r: 64 B at (r/8)*512 + (r%8)*64, 16-byte chunk c4 (8 halves) stored at c4 ^ ((r/2)%4).
-    const int r = threadIdx.x - 384;  // 0..127
+    const int r = threadIdx.x - SPLIT_WARP0 * 32;  // 0..127
     const uint32_t src_row = (r >> 3) * 1024 + (r & 7) * 128, sx = r & 7;
     const uint32_t dst_row = (r >> 3) * 512 + (r & 7) * 64, dx = (r >> 1) & 3;
     uint32_t it = 0;
@@ -236,7 +236,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue (see gemm_tc.cu)
     const int q = warp & 3;            // TMEM lane quarter this warp may read
-    const int half = (warp - 4) >> 2;  // the two warps of a quarter take alternate 16-column sub-chunks
+    const int half = (warp - 4) >> 2;  // the EPI_PARTS warps of a quarter take every EPI_PARTS-th 16-column sub-chunk
     float* stg = reinterpret_cast<float*>(base + S * SM::STAGE + 256) + (warp - 4) * (32 * CP);
     const bool all_al = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
                         (!p.R || ((p.ldr % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.R) & 15) == 0))) &&

@@ -9,10 +9,10 @@
 // over the freshly landed TMA tiles - the swizzled layout is preserved because the op is element-wise),
 // so HBM/L2 only ever carry the fp32 operands once.
 //
-// Roles (512 threads, 1 CTA/SM, persistent over 128 x BN output tiles):
+// Roles (640 threads, 1 CTA/SM, persistent over 128 x BN output tiles):
 //   warp 0        TMA producer            warp 1       tcgen05.mma issuer (one elected lane)
-//   warp 2        TMEM allocator          warps 4-11   epilogue: tcgen05.ld -> bias/act/residual -> global
-//   warps 12-15   splitters (A_lo, W_lo)               (two epilogue warps per TMEM lane quarter)
+//   warp 2        TMEM allocator          warps 4-15   epilogue: tcgen05.ld -> bias/act/residual -> global
+//   warps 16-19   splitters (A_lo, W_lo)               (three epilogue warps per TMEM lane quarter)
 // Pipelines: full[s] (TMA landed) -> split[s] (lo halves written) -> MMA -> empty[s];
 //            tmem_full[a] (tile accumulated) -> epilogue -> tmem_empty[a]  (two TMEM accumulators).
 #include <cuda.h>
@@ -28,7 +28,7 @@ using namespace tcc;
 
 // BK (tc_common.cuh) = 32 floats per k-block = one 128-byte swizzle row
 constexpr int UK = 8;        // UMMA K for tf32 (32 bytes)
-constexpr int NTHREADS = 512;
+constexpr int NTHREADS = TC_THREADS;
 
 // K-major, 128B-swizzled shared-memory operand descriptor (rows of 128 B, 8-row groups 1024 B apart)
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
@@ -91,8 +91,8 @@ struct Smem {
   static constexpr int B_BYTES = BN * BK * 4;
   static constexpr int STAGE = 2 * A_BYTES + 2 * B_BYTES;
   static constexpr int STAGES = (BN == 256) ? 2 : 3;
-  static constexpr int LN_BYTES = 2 * 512 * 4;  // gamma / beta of a LayerNorm folded into A (K <= 512)
-  static constexpr int BYTES = STAGES * STAGE + 1024 /*align*/ + 256 /*barriers*/ + 8 * 32 * CP * 4 /*epilogue*/ + LN_BYTES;
+  static constexpr int LN_BYTES = 2 * 256 * 4;  // gamma / beta of a LayerNorm folded into A (K <= 256)
+  static constexpr int BYTES = STAGES * STAGE + 1024 /*align*/ + 256 /*barriers*/ + EPI_WARPS * 32 * CP * 4 /*epilogue*/ + LN_BYTES;
 };
 
 template <int BN, int ACT, int LNF>
@@ -125,7 +125,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 256);
+      mbar_init(&tempty[i], EPI_WARPS * 32);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -202,9 +202,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         umma_commit(&tfull[acc]);          // accumulator complete
       }
     }
-  } else if (warp >= 12) {
+  } else if (warp >= SPLIT_WARP0) {
     // ------------------------------------------------------------------ splitters: lo = x - tf32(x)
-    const int t = threadIdx.x - 384;  // 0..127
+    const int t = threadIdx.x - SPLIT_WARP0 * 32;  // 0..127
     uint32_t it = 0;
     auto lo4 = [](float4 v) {
       float4 r;
@@ -219,7 +219,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       // (x - mean) rstd gamma + beta before taking the lo part.  gamma / beta of the whole K range sit in shared
       // memory (zero beyond K, where TMA has zero-filled W as well); 16-byte chunk c of a 128-byte swizzle row is
       // stored at c ^ (row % 8), so the eight rows of a quarter-warp hit eight different bank groups.
-      float* gb = reinterpret_cast<float*>(base + S * SM::STAGE + 256 + 8 * 32 * CP * 4);  // [2][KB * BK]
+      float* gb = reinterpret_cast<float*>(base + S * SM::STAGE + 256 + EPI_WARPS * 32 * CP * 4);  // [2][KB * BK]
       const int kpad = KB * BK;
       for (int i = t; i < kpad; i += 128) {
         gb[i] = i < p.K ? p.ln.a_g[i] : 0.f;
@@ -295,7 +295,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     // residual loads and the output store are all full-line, 16-byte-per-lane accesses, and every load
     // of a chunk is issued before the first store (C and R may alias as far as the compiler knows).
     const int q = warp & 3;            // TMEM lane quarter this warp may read
-    const int half = (warp - 4) >> 2;  // the two warps of a quarter take alternate 16-column sub-chunks
+    const int half = (warp - 4) >> 2;  // the EPI_PARTS warps of a quarter take every EPI_PARTS-th 16-column sub-chunk
     float* stg = reinterpret_cast<float*>(base + S * SM::STAGE + 256) + (warp - 4) * (32 * CP);
     const bool all_al = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
                         (!p.R || ((p.ldr % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.R) & 15) == 0))) &&
@@ -353,7 +353,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 
 }  // namespace tc
 
-int ln_stats_parts(int N) { return 2 * cdiv(N, N > 128 ? 256 : 128); }
+int ln_stats_parts(int N) { return tcc::EPI_PARTS * cdiv(N, N > 128 ? 256 : 128); }
 
 // Can this GEMM go through the tensor-core kernel?  (W must be [N,K] K-major.)
 bool gemm_tc_supported(const GemmArgs& a) {
@@ -400,10 +400,10 @@ int launch_gemm_tc(const GemmArgs& a, cudaStream_t st) {
   int lnf = 0;
   if (a.ln.any()) {
     // the fused LayerNorm pieces live in the staged fast path of the epilogue (and in the splitter warps) only
-    EDGL_REQUIRE(a.N % 16 == 0 && a.ldc % 4 == 0 && (!a.R || a.ldr % 4 == 0) && a.ln.L >= 1 && a.K <= 512 &&
+    EDGL_REQUIRE(a.N % 16 == 0 && a.ldc % 4 == 0 && (!a.R || a.ldr % 4 == 0) && a.ln.L >= 1 && (!a.ln.a_rs || a.K <= 256) &&
                      (reinterpret_cast<uintptr_t>(a.C) & 15) == 0 && (!a.R || (reinterpret_cast<uintptr_t>(a.R) & 15) == 0) &&
                      (!a.bias || (reinterpret_cast<uintptr_t>(a.bias) & 15) == 0) && !a.pbias,
-                 "gemm_tc: fused LayerNorm needs N %% 16 == 0, K <= 512 and 16-byte aligned operands");
+                 "gemm_tc: fused LayerNorm needs N %% 16 == 0, K <= 256 for a normalised A, and 16-byte aligned operands");
     EDGL_REQUIRE(!a.ln.a_rs || (a.ln.a_g && a.ln.a_b), "gemm_tc: LayerNorm on A needs gamma and beta");
     EDGL_REQUIRE(!a.ln.r_rs || (a.R && a.ln.r_g && a.ln.r_b), "gemm_tc: LayerNorm on the residual needs R, gamma, beta");
     p.epi_direct = 0;

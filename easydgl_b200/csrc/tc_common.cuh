@@ -73,6 +73,18 @@ __device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, uint32_t (&r)
 }
 
 // ---------------------------------------------------------------------------------------------- epilogue
+// Warp roles of both kernels: warps 0-3 control (TMA producer, MMA issuer, TMEM allocator, spare), then EPI_WARPS
+// epilogue warps (EPI_PARTS per TMEM lane quarter, taking every EPI_PARTS-th 16-column chunk), then 4 splitter warps.
+// The layers are bound by their epilogues (bias / GELU / residual / LayerNorm pieces on 128 x BN fp32 values per tile
+// with TMEM -> shared -> global hops in between), so the epilogue gets 12 warps; setmaxnreg moves the registers the
+// control and splitter warps do not need over to them.
+#ifndef EDGL_EPI_PARTS
+#define EDGL_EPI_PARTS 3
+#endif
+constexpr int EPI_PARTS = EDGL_EPI_PARTS;
+constexpr int EPI_WARPS = 4 * EPI_PARTS;
+constexpr int SPLIT_WARP0 = 4 + EPI_WARPS;
+constexpr int TC_THREADS = (SPLIT_WARP0 + 4) * 32;
 constexpr int BM = 128;      // UMMA M of both kernels
 constexpr int CW = 16;       // epilogue sub-chunk width (columns per tcgen05.ld)
 constexpr int CP = CW + 4;   // padded pitch of the epilogue staging tile
@@ -101,7 +113,7 @@ __device__ __forceinline__ float gelu_erf_exact(float x) {
   return x * (0.5f * (1.0f + erff(x * 0.70710678118654752440f)));  // EasyDGL.py:31-32
 }
 
-// One 128 x BN accumulator tile -> global memory, for one epilogue warp (TMEM lane quarter q, column half `half`).
+// One 128 x BN accumulator tile -> global memory, for one epilogue warp (TMEM lane quarter q, column part `part`).
 // Two paths per 16-column chunk:
 //  * staged: tcgen05.ld hands every thread one accumulator ROW; writing rows straight to global would cost 32 cache
 //    lines per instruction, so the 32x16 chunk is transposed through a padded shared-memory tile and handled 8 rows x
@@ -115,7 +127,7 @@ __device__ __forceinline__ float gelu_erf_exact(float x) {
 constexpr int LN_A = 1, LN_RES = 2, LN_STATS = 4, LN_LAST = 8;
 
 template <int BN, int ACT, bool SCALED, int LNF = 0, class P>
-__device__ __forceinline__ void epilogue_tile(const P& p, uint32_t tmem_acc, int m0, int n0, int q, int half, int lane,
+__device__ __forceinline__ void epilogue_tile(const P& p, uint32_t tmem_acc, int m0, int n0, int q, int part, int lane,
                                               float* stg, bool all_al, const int (&pbo)[4], const int (&pbd)[4], float inv,
                                               float& cmax) {
   constexpr int LPR = CW / 4;        // lanes per row (4)
@@ -149,7 +161,7 @@ __device__ __forceinline__ void epilogue_tile(const P& p, uint32_t tmem_acc, int
     }
   }
 #pragma unroll 1
-  for (int c0 = half * CW; c0 < BN; c0 += 2 * CW) {
+  for (int c0 = part * CW; c0 < BN; c0 += EPI_PARTS * CW) {
     if (LNF == 0 && p.epi_direct && all_al && n0 + c0 + CW <= p.N) {
       // ---- direct path: two 16-row halves; every store instruction writes 8 rows x one 32-byte sector
       const int g = lane >> 2, t2 = (lane & 3) * 2;
@@ -279,14 +291,14 @@ __device__ __forceinline__ void epilogue_tile(const P& p, uint32_t tmem_acc, int
   if constexpr ((LNF & LN_STATS) != 0) {
     // the four lanes of a row hold its partial sums over this warp's column chunks: one (sum, sum of squares) pair
     // per (row, n-tile, column half), added in a fixed order (deterministic)
-    const int nparts = 2 * ((p.N + BN - 1) / BN), part = 2 * (n0 / BN) + half;
+    const int nparts = EPI_PARTS * ((p.N + BN - 1) / BN), pidx = EPI_PARTS * (n0 / BN) + part;
 #pragma unroll
     for (int itr = 0; itr < NIT; ++itr) {
       float s = st_s[itr], q2 = st_q[itr];
       s += __shfl_xor_sync(0xffffffffu, s, 1); q2 += __shfl_xor_sync(0xffffffffu, q2, 1);
       s += __shfl_xor_sync(0xffffffffu, s, 2); q2 += __shfl_xor_sync(0xffffffffu, q2, 2);
       const int row = rbase + RPI * itr;
-      if ((lane % LPR) == 0 && row < p.M) p.ln.stats[(size_t)row * nparts + part] = make_float2(s, q2);
+      if ((lane % LPR) == 0 && row < p.M) p.ln.stats[(size_t)row * nparts + pidx] = make_float2(s, q2);
     }
   }
 }

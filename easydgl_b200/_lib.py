@@ -45,6 +45,8 @@ _SIGS = {
     "edgl_forward_topk_host": (_I, [_P, _P, _P, _I, _I, _P, _P, _P]),
     "edgl_forward_topk_host_submit": (_I, [_P, _P, _P, _I, _I, _P, _P, _P]),
     "edgl_forward_topk_host_wait": (_I, [_P, _I]),
+    "edgl_forward_train_logits": (_I, [_P, _P, _P, _I, _P, _I, _P, _P]),
+    "edgl_forward_train_loss": (_I, [_P, _P, _P, _I, _P, _P, _I, C.c_float, C.c_float, _P, _P]),
     "edgl_encode": (_I, [_P, _P, _P, _I, _P, _P]),
     "edgl_encode_packed": (_I, [_P, _P, _P, _I, _P, C.c_int64, _P]),
     "edgl_logits_topk": (_I, [_P, _P, C.c_int64, _P, _I, C.c_int64, _I, C.c_int64, _P, _P, _P]),

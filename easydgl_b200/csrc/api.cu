@@ -89,6 +89,12 @@ struct edgl_handle {
   float2* ln_parts = nullptr;                      // [rows][parts] row partial sums
   float2 *ln_rs1 = nullptr, *ln_rs2 = nullptr, *ln_rs3 = nullptr;  // [max_batch] (mean, rstd)
   float* tr_last = nullptr;                        // [max_batch, d] last rows of the transform layer
+  // training-mode forward (train.cu): allocated on first use (grow-only)
+  std::vector<float*> train_lam;   // per block: lam [h * max_batch, L, E]
+  float* train_y = nullptr;        // gathered hidden rows [rows_cap, d]
+  float *train_pe = nullptr, *train_wt = nullptr, *train_tpp = nullptr;  // [rows_cap], [rows_cap], [3][h * rows_cap]
+  long long train_rows_cap = 0;
+  double* train_acc = nullptr;     // reduction slots
   // workspace (owned)
   float *xa = nullptr, *p0 = nullptr, *p1 = nullptr, *p2 = nullptr, *qkvt = nullptr, *spans = nullptr, *y = nullptr,
         *logits_ws = nullptr;
@@ -256,8 +262,15 @@ EmbedArgs embed_args(const edgl_handle* h, const int64_t* ids, const float* ts, 
   return e;
 }
 
+// training-mode forward: the encoder also hands out the full LayerNorm'ed hidden states and every block's intensities
+struct TrainOut {
+  float* Y = nullptr;               // [B*L, d]
+  std::vector<float*> lam;          // per block [h*B, L, E], or empty
+};
+
 // EasyDGL.__call__ up to y = hidden[:, -1]  (EasyDGL.py:69-146)
-int encode_easydgl(edgl_handle* h, const int64_t* ids, const float* ts, int B, float* y, long long ldy, cudaStream_t st) {
+int encode_easydgl(edgl_handle* h, const int64_t* ids, const float* ts, int B, float* y, long long ldy, cudaStream_t st,
+                   const TrainOut* tr = nullptr) {
   const int d = h->d, L = h->L;
   const long long rows = (long long)B * L;
   EmbedArgs e = embed_args(h, ids, ts, B);
@@ -290,7 +303,8 @@ int encode_easydgl(edgl_handle* h, const int64_t* ids, const float* ts, int B, f
       EDGL_TRY(dense_nk(cur, ldcur, h->btT[i].at("qkvt_w"), d, F(w, "qkvt_b"), h->qkvt, 4 * d, rows, 4 * d, ACT_NONE,
                         nullptr, 0, st, true, w16(i, "qkvt_w", 0), am + AMAX_LN2));
     }
-    AttnArgs a = attn_args(h, w, h->qkvt, h->kmask, h->spans, h->marks, cur, ldcur, h->p0, nullptr, B, false, true);
+    AttnArgs a = attn_args(h, w, h->qkvt, h->kmask, h->spans, h->marks, cur, ldcur, h->p0,
+                           (tr && !tr->lam.empty()) ? tr->lam[i] : nullptr, B, false, true);
     bool att_amax = false;
     if (f16) { a.out_amax = am + AMAX_ATT; a.amax_published = &att_amax; }
     mark(h, ST_ATTENTION, st);
@@ -298,7 +312,7 @@ int encode_easydgl(edgl_handle* h, const int64_t* ids, const float* ts, int B, f
     // a fallback attention kernel (shape not covered at run time) does not publish max|O|: take it in a pass of
     // its own rather than feed the scaled 3xFP16 attention-out GEMM a zero maximum
     if (f16 && (h->f16_mask & 2) && !att_amax) EDGL_TRY(launch_absmax(h->p0, rows * d, am + AMAX_ATT, st));
-    if (h->ln_fuse) {
+    if (h->ln_fuse && !tr) {
       // LayerNorm statistics from the producing GEMM's epilogue, applied by the consumers (LnEpi, common.cuh): no
       // LayerNorm pass reads or writes the activations
       const bool last = (i == h->cfg.num_blocks - 1);
@@ -365,6 +379,11 @@ int encode_easydgl(edgl_handle* h, const int64_t* ids, const float* ts, int B, f
   EDGL_TRY(dense_nk(cur, ldcur, h->mtT.at("tr_w"), d, F(h->mt, "tr_b"), h->p0, d, rows, d, ACT_GELU, nullptr, 0, st, true,
                     (f16 && (h->f16_mask & 16)) ? h->mt16.at("tr_w") : nullptr, am + AMAX_LN2));  // :138
   mark(h, ST_LN_OUT, st);
+  if (tr) {  // every position is needed (EasyDGL.py:141: batch_gather at the masked positions)
+    EDGL_TRY(launch_layernorm(h->p0, F(h->mt, "tr_ln_g"), F(h->mt, "tr_ln_b"), B, L, d, tr->Y, false, st));
+    mark(h, ST_END, st);
+    return 0;
+  }
   EDGL_TRY(launch_layernorm(h->p0, F(h->mt, "tr_ln_g"), F(h->mt, "tr_ln_b"), B, L, d, y, true, st,
                             (f16 && y == h->y) ? am + AMAX_Y : nullptr, ldy));            // :139,146
   mark(h, ST_END, st);
@@ -372,7 +391,8 @@ int encode_easydgl(edgl_handle* h, const int64_t* ids, const float* ts, int B, f
 }
 
 // CTSMA.__call__ up to y (CTSMA.py:46-87)
-int encode_ctsma(edgl_handle* h, const int64_t* ids, const float* ts, int B, float* y, long long ldy, cudaStream_t st) {
+int encode_ctsma(edgl_handle* h, const int64_t* ids, const float* ts, int B, float* y, long long ldy, cudaStream_t st,
+                 const TrainOut* tr = nullptr) {
   const int d = h->d, L = h->L;
   const long long rows = (long long)B * L;
   EmbedArgs e = embed_args(h, ids, ts, B);
@@ -390,7 +410,8 @@ int encode_ctsma(edgl_handle* h, const int64_t* ids, const float* ts, int B, flo
                       st));
     EDGL_TRY(dense_nk(cur, cin, h->btT[i].at("kvt_w"), cin, h->bkvt[i], h->qkvt + d, 4 * d, rows, 3 * d, ACT_NONE,
                       nullptr, 0, st));                                                  // temporal.py:340-343
-    AttnArgs a = attn_args(h, w, h->qkvt, h->kmask, h->spans, h->marks, h->p0, cin, h->p1, nullptr, B, true, false);
+    AttnArgs a = attn_args(h, w, h->qkvt, h->kmask, h->spans, h->marks, h->p0, cin, h->p1,
+                           (tr && !tr->lam.empty()) ? tr->lam[i] : nullptr, B, true, false);
     mark(h, ST_ATTENTION, st);
     EDGL_TRY(launch_attention(a, st));                                                   // temporal.py:345-385
     mark(h, ST_LN_ATT, st);
@@ -403,16 +424,58 @@ int encode_ctsma(edgl_handle* h, const int64_t* ids, const float* ts, int B, flo
     cin = d;
   }
   mark(h, ST_LN_OUT, st);
+  if (tr) {  // CTSMA.py:80,83: every position is predicted in training
+    EDGL_TRY(launch_layernorm(cur, F(h->mt, "out_ln_g"), F(h->mt, "out_ln_b"), B, L, d, tr->Y, false, st));
+    mark(h, ST_END, st);
+    return 0;
+  }
   EDGL_TRY(launch_layernorm(cur, F(h->mt, "out_ln_g"), F(h->mt, "out_ln_b"), B, L, d, y, true, st, nullptr, ldy));  // CTSMA.py:80,87
   mark(h, ST_END, st);
   return 0;
 }
 
-int encode(edgl_handle* h, const int64_t* ids, const float* ts, int B, float* y, cudaStream_t st, long long ldy = 0) {
+int encode(edgl_handle* h, const int64_t* ids, const float* ts, int B, float* y, cudaStream_t st, long long ldy = 0,
+           const TrainOut* tr = nullptr) {
   if (B == 0) return 0;
   if (ldy == 0) ldy = h->d;
-  return h->cfg.model == EDGL_MODEL_EASYDGL ? encode_easydgl(h, ids, ts, B, y, ldy, st)
-                                            : encode_ctsma(h, ids, ts, B, y, ldy, st);
+  return h->cfg.model == EDGL_MODEL_EASYDGL ? encode_easydgl(h, ids, ts, B, y, ldy, st, tr)
+                                            : encode_ctsma(h, ids, ts, B, y, ldy, st, tr);
+}
+
+// Encoder in training mode + the hidden rows that are predicted: Yg [B*M, d] (gathered at `positions`, or every row
+// when positions == null and M == L).  Grows the handle's training buffers on demand.
+int train_encode(edgl_handle* h, const int64_t* ids, const float* ts, int B, const int64_t* positions, int M,
+                 bool want_lam, const float** Yg, cudaStream_t st) {
+  const long long rows = (long long)B * M;
+  const int nb = h->cfg.num_blocks;
+  if (rows > h->train_rows_cap) {
+    const long long cap = (long long)h->cfg.max_batch * (M > h->L ? M : h->L);
+    float* p = nullptr;
+    EDGL_TRY(dev_alloc(h, &p, (size_t)cap * h->d)); h->train_y = p;
+    EDGL_TRY(dev_alloc(h, &p, (size_t)cap)); h->train_pe = p;
+    EDGL_TRY(dev_alloc(h, &p, (size_t)cap)); h->train_wt = p;
+    EDGL_TRY(dev_alloc(h, &p, (size_t)3 * h->h * cap)); h->train_tpp = p;
+    h->train_rows_cap = cap;
+  }
+  if (!h->train_acc) EDGL_TRY(dev_alloc(h, &h->train_acc, (size_t)(3 + 3 * nb)));
+  TrainOut tr;
+  tr.Y = h->p1;  // free after the last dense layer of either model
+  if (want_lam) {
+    if ((int)h->train_lam.size() != nb) h->train_lam.assign(nb, nullptr);
+    for (int i = 0; i < nb; ++i)
+      if (!h->train_lam[i]) EDGL_TRY(dev_alloc(h, &h->train_lam[i], (size_t)h->h * h->cfg.max_batch * h->L * h->E));
+    tr.lam = h->train_lam;
+  }
+  if (h->cfg.model == EDGL_MODEL_CTSMA) tr.Y = h->p0;  // CTSMA's last block leaves its output in p2
+  EDGL_TRY(encode(h, ids, ts, B, nullptr, st, 0, &tr));
+  if (positions) {
+    EDGL_CUDA(cudaMemsetAsync(h->flag, 0, sizeof(int), st));
+    EDGL_TRY(launch_gather_rows(tr.Y, positions, h->L, M, h->d, rows, h->train_y, h->flag, st));
+    *Yg = h->train_y;
+  } else {
+    *Yg = tr.Y;
+  }
+  return 0;
 }
 
 // logits[r0:r0+rc, c0:c1] = y @ table[c0:c1]^T + bias   (EasyDGL.py:149-150 / CTSMA.py:89-90, Base.py:106-110)
@@ -847,6 +910,94 @@ int edgl_forward_logits(edgl_handle* h, const int64_t* seqs_i, const float* seqs
   mark(h, ST_LOGITS_GEMM, st);
   EDGL_TRY(logits_rows(h, h->y, h->d, B, logits, (int)(h->c1 - h->c0), st));
   mark(h, ST_END, st);
+  return 0;
+}
+
+static int check_train_args(edgl_handle* h, int B, const int64_t* positions, int M) {
+  EDGL_TRY(check_ready(h, B));
+  EDGL_REQUIRE(h->cfg.shard_world == 1, "the training-mode forward needs an unsharded handle");
+  if (h->cfg.model == EDGL_MODEL_EASYDGL)
+    EDGL_REQUIRE(positions && M >= 1 && M <= h->L, "EasyDGL training needs masked_positions [B, M], 1 <= M <= L");
+  else
+    EDGL_REQUIRE(!positions && M == h->L, "CTSMA predicts every position in training: positions = NULL, M = seqslen");
+  return 0;
+}
+
+int edgl_forward_train_logits(edgl_handle* h, const int64_t* seqs_i, const float* seqs_t, int B,
+                              const int64_t* masked_positions, int M, float* logits, void* stream) {
+  EDGL_TRY(check_train_args(h, B, masked_positions, M));
+  if (!seqs_i || !seqs_t || !logits) return set_error(EDGL_EINVAL, "null argument");
+  if (B == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const float* Yg = nullptr;
+  EDGL_TRY(train_encode(h, seqs_i, seqs_t, B, masked_positions, M, false, &Yg, st));
+  mark(h, ST_LOGITS_GEMM, st);
+  EDGL_TRY(logits_rows(h, Yg, h->d, (long long)B * M, logits, (int)(h->c1 - h->c0), st));
+  mark(h, ST_END, st);
+  int flag = 0;
+  EDGL_CUDA(cudaMemcpyAsync(&flag, h->flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+  EDGL_CUDA(cudaStreamSynchronize(st));
+  if (masked_positions && flag) return set_error(EDGL_EINVAL, "masked_positions holds values outside [0, L)");
+  return 0;
+}
+
+int edgl_forward_train_loss(edgl_handle* h, const int64_t* seqs_i, const float* seqs_t, int B,
+                            const int64_t* masked_positions, const int64_t* labels, int M, float l2_reg, float ct_reg,
+                            float* loss_out, void* stream) {
+  EDGL_TRY(check_train_args(h, B, masked_positions, M));
+  if (!seqs_i || !seqs_t || !labels || !loss_out) return set_error(EDGL_EINVAL, "null argument");
+  EDGL_REQUIRE(l2_reg >= 0.f, "Setting a scale less than 0 on a regularizer: %g.", (double)l2_reg);  // coding.py:27-29
+  if (B == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool easy = h->cfg.model == EDGL_MODEL_EASYDGL;
+  const int nb = h->cfg.num_blocks, d = h->d;
+  const long long rows = (long long)B * M;
+  const float* Yg = nullptr;
+  EDGL_TRY(train_encode(h, seqs_i, seqs_t, B, masked_positions, M, ct_reg != 0.f, &Yg, st));
+  // ---- masked softmax cross entropy over the item catalogue, the logits materialised in workspace-sized chunks
+  const int Ns = (int)(h->c1 - h->c0);
+  const int ldw = (Ns + 3) & ~3;
+  if (!masked_positions) EDGL_CUDA(cudaMemsetAsync(h->flag, 0, sizeof(int), st));
+  for (long long r0 = 0; r0 < rows; r0 += h->ws_rows) {
+    const long long rc = (rows - r0 < h->ws_rows) ? (rows - r0) : h->ws_rows;
+    mark(h, ST_LOGITS_GEMM, st);
+    EDGL_TRY(logits_rows(h, Yg + r0 * d, d, rc, h->logits_ws, ldw, st));
+    mark(h, ST_END, st);
+    EDGL_TRY(launch_ce_rows(h->logits_ws, ldw, Ns, labels, r0, (int)rc, h->train_pe, h->train_wt, h->flag, st));
+  }
+  double* acc = h->train_acc;
+  EDGL_TRY(launch_reduce(h->train_pe, rows, 0, 1.0, acc + 0, 0, st));
+  EDGL_TRY(launch_reduce(h->train_wt, rows, 0, 1.0, acc + 1, 0, st));
+  // ---- tf.losses.get_regularization_loss(): the embedding tables built with l2_reg (raw variables, row 0 included)
+  EDGL_CUDA(cudaMemsetAsync(acc + 2, 0, sizeof(double), st));
+  if (l2_reg != 0.f) {
+    EDGL_TRY(launch_reduce(F(h->mt, "item_embs"), (long long)h->N1 * d, 1, 0.5 * l2_reg, acc + 2, 1, st));
+    EDGL_TRY(launch_reduce(F(h->mt, "pos_embs"), (long long)h->L * d, 1, 0.5 * l2_reg, acc + 2, 1, st));
+    if (easy) EDGL_TRY(launch_reduce(F(h->mt, "mark_embs"), (long long)h->E * d, 1, 0.5 * l2_reg, acc + 2, 1, st));
+  }
+  // ---- continuous-time regulariser: one biased likelihood per block (collection "LLE_PP")
+  int nct = 0;
+  if (ct_reg != 0.f) {
+    const long long n = (long long)h->h * rows;
+    float* ell = h->train_tpp;
+    float* nu = ell + (size_t)h->h * h->train_rows_cap;
+    float* cnt = nu + (size_t)h->h * h->train_rows_cap;
+    for (int i = 0; i < nb; ++i) {
+      EDGL_TRY(launch_tpp_terms(h->train_lam[i], masked_positions, labels, h->mark8, h->cfg.mark_rows, seqs_t, h->ts_len, B,
+                                h->L, M, h->h, h->E, ell, nu, cnt, st));
+      EDGL_TRY(launch_reduce(ell, n, 0, 1.0, acc + 3 + 3 * i + 0, 0, st));
+      EDGL_TRY(launch_reduce(nu, n, 0, 1.0, acc + 3 + 3 * i + 1, 0, st));
+      EDGL_TRY(launch_reduce(cnt, n, 0, 1.0, acc + 3 + 3 * i + 2, 0, st));
+    }
+    nct = nb;
+  }
+  // EasyDGL divides the regulariser by the number of heads (EasyDGL.py:175), CTSMA does not (CTSMA.py:110)
+  EDGL_TRY(launch_loss_combine(acc, nct, (double)ct_reg / (easy ? (double)h->h : 1.0), loss_out, st));
+  int flag = 0;
+  EDGL_CUDA(cudaMemcpyAsync(&flag, h->flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+  EDGL_CUDA(cudaStreamSynchronize(st));
+  if (flag == 1) return set_error(EDGL_EINVAL, "masked_positions holds values outside [0, L)");
+  if (flag == 2) return set_error(EDGL_EINVAL, "labels hold values outside [0, num_items)");
   return 0;
 }
 

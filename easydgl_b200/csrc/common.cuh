@@ -185,6 +185,17 @@ int launch_intensity(const float* H, const float* spans, const uint8_t* marks, c
 int launch_layernorm(const float* x, const float* gamma, const float* beta, int B, int L, int C, float* out,
                      bool last_only, cudaStream_t st, unsigned int* out_amax = nullptr, long long out_stride = 0);
 
+// training-mode forward (train.cu)
+int launch_gather_rows(const float* Y, const int64_t* pos, int L, int M, int d, long long rows, float* out, int* err,
+                       cudaStream_t st);
+int launch_ce_rows(const float* logits, int ld, int N, const int64_t* labels, long long row0, int rows, float* pe,
+                   float* wt, int* err, cudaStream_t st);
+int launch_tpp_terms(const float* lam, const int64_t* positions, const int64_t* labels, const uint8_t* mark8,
+                     int mark_rows, const float* ts, int ts_len, int B, int L, int M, int heads, int E, float* ell,
+                     float* nu, float* cnt, cudaStream_t st);
+int launch_reduce(const float* x, long long n, int squares, double scale, double* out, int accumulate, cudaStream_t st);
+int launch_loss_combine(const double* acc, int num_blocks, double ct_scale, float* loss_out, cudaStream_t st);
+
 int launch_mask_seen(float* logits, int ld, int B, const int64_t* ids, int seen_len, long long seen_stride,
                      long long col0, long long col1, cudaStream_t st);
 // Fused candidate exchange over peer memory (multi-GPU): when `dest` is set the top-K kernel writes row R's

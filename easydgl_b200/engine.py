@@ -181,6 +181,43 @@ class Engine:
         if idx_cpu.numel() < B * self.K or val_cpu.numel() < B * self.K:
             raise ValueError("output buffers too small")
 
+    # ------------------------------------------------------------------ training-mode forward
+    def _train_args(self, seqs_i, seqs_t, masked_positions):
+        seqs_i, seqs_t, B = self._inputs(seqs_i, seqs_t)
+        if self.cfg.model == "EasyDGL":
+            if masked_positions is None:
+                raise ValueError("EasyDGL training needs features['masked_positions'] (dataloader.py:181-201)")
+            pos = _req(masked_positions, torch.int64, "masked_positions", self.device)
+            if pos.dim() != 2 or pos.shape[0] != B:
+                raise ValueError("masked_positions must be [B, masklen]")
+            return seqs_i, seqs_t, B, pos, int(pos.shape[1])
+        if masked_positions is not None:
+            raise ValueError("CTSMA predicts every position in training (CTSMA.py:82-83): no masked_positions")
+        return seqs_i, seqs_t, B, None, self.L
+
+    def forward_train_logits(self, seqs_i, seqs_t, masked_positions=None) -> torch.Tensor:
+        """model(features, is_training=True) with dropout 0: logits [B*M, N] at the predicted positions."""
+        seqs_i, seqs_t, B, pos, M = self._train_args(seqs_i, seqs_t, masked_positions)
+        out = torch.empty((B * M, self.c1 - self.c0), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.edgl_forward_train_logits(self._handle, seqs_i.data_ptr(), seqs_t.data_ptr(), B, _ptr(pos), M,
+                                                     out.data_ptr(), _stream()))
+        return out
+
+    def forward_train_loss(self, seqs_i, seqs_t, labels, masked_positions=None, l2_reg: float = 0.,
+                           ct_reg: float = 0.) -> torch.Tensor:
+        """The loss of model.train (dropout 0): tensor [4] = (loss, cross entropy, l2 term, continuous-time term)."""
+        seqs_i, seqs_t, B, pos, M = self._train_args(seqs_i, seqs_t, masked_positions)
+        labels = _req(labels, torch.int64, "labels", self.device)
+        if tuple(labels.shape) != (B, M):
+            raise ValueError("labels must be [B, %d] (got %s)" % (M, tuple(labels.shape)))
+        out = torch.empty(4, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.edgl_forward_train_loss(self._handle, seqs_i.data_ptr(), seqs_t.data_ptr(), B, _ptr(pos),
+                                                   labels.data_ptr(), M, float(l2_reg), float(ct_reg), out.data_ptr(),
+                                                   _stream()))
+        return out
+
     def encode(self, seqs_i, seqs_t) -> torch.Tensor:
         seqs_i, seqs_t, B = self._inputs(seqs_i, seqs_t)
         y = torch.empty((B, self.d), dtype=torch.float32, device=self.device)

@@ -102,13 +102,31 @@ class Sequential(object):
     def __call__(self, features, is_training):
         raise NotImplementedError("the model is not implemented")  # Base.py:117
 
+    def _check_no_dropout(self):
+        if self.hidden_dropout_rate or self.attention_probs_dropout_rate:
+            raise NotImplementedError(
+                "training-mode forward with dropout > 0 is not implemented: TensorFlow's random stream "
+                "(EasyDGL.py:92,114,126; temporal.py:442) cannot be reproduced; set both dropout rates to 0")
+
     def train(self, features, labels):
-        raise NotImplementedError("training (backward/optimizer) is out of scope for this hot path (SURVEY 8f)")
+        """The forward half of ``Model.train`` (EasyDGL.py:153-189 / CTSMA.py:93-124 / Base.py:119-131): returns the
+        scalar ``loss`` tensor (masked softmax cross entropy + l2 regulariser + ct_reg * TPP likelihood) and a dict of
+        its parts.  The reference returns ``(train_op, loss_op, loss_init_op)``; the backward pass and the Adam step
+        (Base.py:142-144) are outside this library's scope."""
+        self._check_no_dropout()
+        ids, ts = features['seqs_i'], features['seqs_t']
+        eng = self._get_engine(ids.shape[0])
+        out = eng.forward_train_loss(ids, ts, labels, features.get('masked_positions'), float(self.l2_reg or 0.),
+                                     float(getattr(self, 'ct_reg', 0.) or 0.))
+        return out[0], {"ce": out[1], "l2": out[2], "ct": out[3]}
 
     def _forward(self, features, is_training):
-        if is_training:
-            raise NotImplementedError("training-mode forward is out of scope (SURVEY 8f)")
         ids, ts = features['seqs_i'], features['seqs_t']
+        if is_training:
+            # model(features, is_training=True): logits at the predicted positions, [B * masklen, N]
+            # (EasyDGL.py:140-151) or [B * seqslen, N] (CTSMA.py:82-91); dropout rates must be 0
+            self._check_no_dropout()
+            return self._get_engine(ids.shape[0]).forward_train_logits(ids, ts, features.get('masked_positions'))
         return self._get_engine(ids.shape[0]).forward_logits(ids, ts)
 
     def eval(self, features, labels, mask_seen=True):

@@ -116,6 +116,29 @@ def make_inputs(cfg, batch: int, seed: int = SEED, min_len: int = 5, edge_cases:
                 labels=torch.from_numpy(labels))
 
 
+def make_train_inputs(cfg, batch: int, seed: int = SEED, masklen: int = None):
+    """Training-mode features / labels with the reference's post-processors.  EasyDGL (MAUPostProcessor.mask_random,
+    dataloader.py:181-201): `masklen` distinct positions in 1..T-1 become [MASK], labels = the tokens there (0 on
+    padding: weight 0 in the loss); CTSMA (RegressivePostProcessor, dataloader.py:95-98): seqs_i = tokens[:-1],
+    labels = tokens[1:].  Returns dict(seqs_i, seqs_t, labels[, masked_positions])."""
+    rng = np.random.default_rng(seed + 7)
+    base = make_inputs(cfg, batch, seed=seed)
+    if cfg.model != "EasyDGL":
+        # make_inputs built tokens [B, S+1]; seqs_i = tokens[:, :-1], labels_last = tokens[:, -1]
+        tokens = torch.cat([base["seqs_i"], base["labels"].unsqueeze(1)], dim=1)
+        return dict(seqs_i=tokens[:, :-1].contiguous(), seqs_t=base["seqs_t"], labels=tokens[:, 1:].contiguous())
+    T = cfg.ts_len
+    M = int(masklen if masklen is not None else getattr(cfg, "masklen", 6))
+    tokens = base["seqs_i"].clone()
+    tokens[:, -1] = base["labels"]                        # undo mask_last: the raw sequence
+    pos = np.stack([rng.choice(T - 1, M, replace=False) + 1 for _ in range(batch)]).astype(np.int64)  # dataloader.py:34-36
+    pos = torch.from_numpy(pos)
+    labels = torch.gather(tokens, 1, pos)
+    masked = tokens.clone()
+    masked.scatter_(1, pos, cfg.mask_id)
+    return dict(seqs_i=masked, seqs_t=base["seqs_t"], labels=labels, masked_positions=pos)
+
+
 def make_mark_table(cfg, seed: int = SEED, onehot: bool = False) -> torch.Tensor:
     """int64 [num_items, E] multi-hot item->event-mark table standing in for mark.pkl
     (EasyDGL.py:45): row 0 (padding) all-zero, every item 1-3 marks (exactly 1 if onehot)."""

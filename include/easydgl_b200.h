@@ -125,6 +125,23 @@ int edgl_forward_topk_host_submit(edgl_handle* h, const int64_t* seqs_i_host, co
                                   int mask_seen, int32_t* idx_host, float* val_host, void* stream);
 int edgl_forward_topk_host_wait(edgl_handle* h, int slot);
 
+/* ---- training-mode forward: model(features, is_training=True) and the loss of model.train() ----
+ * Both dropout rates must be 0 (a TF-identical random stream cannot be reproduced; the backward pass and the
+ * optimizer step are outside this library).  EasyDGL: masked_positions int64 [B,M] (features['masked_positions'],
+ * dataloader.py:181-201), labels int64 [B,M]; CTSMA: masked_positions = NULL, M = seqslen, labels int64 [B,S]
+ * (dataloader.py:95-98).  Unsharded handles only. */
+/* logits [B*M, N1] at the predicted positions (EasyDGL.py:140-151 / CTSMA.py:82-91). */
+int edgl_forward_train_logits(edgl_handle* h, const int64_t* seqs_i, const float* seqs_t, int B,
+                              const int64_t* masked_positions, int M, float* logits, void* stream);
+/* The scalar loss of model.train (EasyDGL.py:153-189 / CTSMA.py:93-124): masked softmax cross entropy
+ * -log(softmax + 1e-5) over labels != 0, plus l2_reg * l2_loss of the embedding tables (coding.py:13-44), plus
+ * ct_reg * MAU.biased_likelihood (temporal.py:317-333) of every block's intensities.  loss_out: DEVICE float[4] =
+ * {loss, cross entropy, l2 regulariser, continuous-time regulariser}.  Synchronises the stream (it reports
+ * out-of-range positions / labels). */
+int edgl_forward_train_loss(edgl_handle* h, const int64_t* seqs_i, const float* seqs_t, int B,
+                            const int64_t* masked_positions, const int64_t* labels, int M, float l2_reg, float ct_reg,
+                            float* loss_out, void* stream);
+
 /* ---- the two halves of the forward, for the column-sharded multi-GPU path ---- */
 /* Encoder up to y = hidden[:, -1]  [B,d]  (EasyDGL.py:69-146 / CTSMA.py:46-87). */
 int edgl_encode(edgl_handle* h, const int64_t* seqs_i, const float* seqs_t, int B, float* y, void* stream);

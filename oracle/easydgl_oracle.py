@@ -366,6 +366,88 @@ def forward(seqs_i, seqs_t, W, cfg, **kw):
 
 
 # ----------------------------------------------------------------------------
+# training-mode forward: Model.train() up to the loss (dropout rates 0; the backward pass / Adam are not restated)
+# ----------------------------------------------------------------------------
+def biased_likelihood(mark_intensity: torch.Tensor, next_mark_onehot: torch.Tensor, intervals: torch.Tensor):
+    """MAU.biased_likelihood (temporal.py:317-333).  mark_intensity [hN,Tq,E]; next_mark_onehot [hN,Tq,E];
+    intervals [hN,Tq]."""
+    mi = mark_intensity * torch.sign(next_mark_onehot.sum(dim=2, keepdim=True))          # :321
+    event_intensity = (mi * next_mark_onehot).sum(dim=2)                                 # :322
+    event_ll = torch.log(torch.where(event_intensity == 0, torch.ones_like(event_intensity), event_intensity))  # :324
+    event_ll = event_ll.sum()                                                            # :325
+    entire_intensity = mi.sum(dim=2)                                                     # :327
+    non_event_ll = (entire_intensity * intervals * .5).sum()                             # :328-329
+    num_events = next_mark_onehot.sum()                                                  # :331
+    return -(event_ll - non_event_ll) / num_events                                       # :332
+
+
+def l2_regularization(W: dict, cfg, l2_reg: float, dtype) -> torch.Tensor:
+    """tf.losses.get_regularization_loss(): l2_reg * tf.nn.l2_loss(table) = l2_reg * sum(table**2) / 2 for every
+    C.Embedding table built with l2_reg (coding.py:13-44,48,55): item_embs, spatial_embs (and mark_embs for
+    EasyDGL, EasyDGL.py:50-54; CTSMA.py:33-35).  The regulariser sees the raw variable (row 0 included)."""
+    if l2_reg == 0.:
+        return torch.zeros((), dtype=dtype)
+    names = ["item_embs", "pos_embs"] + (["mark_embs"] if cfg.model == "EasyDGL" else [])
+    tot = torch.zeros((), dtype=dtype)
+    for n in names:
+        tot = tot + l2_reg * (W[n].to(dtype) ** 2).sum() / 2
+    return tot
+
+
+def train_forward(seqs_i, seqs_t, labels, W, cfg, masked_positions=None, l2_reg=0., ct_reg=0.,
+                  dtype=torch.float64, return_logits=False):
+    """Model.train(features, labels) up to `loss` with both dropout rates 0 (EasyDGL.py:140-189, CTSMA.py:82-124).
+    EasyDGL: features carry `masked_positions` [B,M] (dataloader.py:181-201), labels [B,M]; CTSMA: every position
+    is predicted, labels [B,S] (dataloader.py:95-98).  Returns dict(loss, ce, l2, ct[, logits])."""
+    out = forward(seqs_i, seqs_t, W, cfg, dtype=dtype, return_all=True)
+    Wd = _cast(W, dtype)
+    h = cfg.num_heads
+    B = seqs_i.shape[0]
+    if cfg.model == "EasyDGL":
+        Y = gelu(out.last_hidden @ Wd["tr_w"] + Wd["tr_b"])                              # :138
+        Y = layernorm(Y, Wd["tr_ln_g"], Wd["tr_ln_b"])                                   # :139
+        pos = masked_positions.long()
+        Yg = torch.gather(Y, 1, pos.unsqueeze(-1).expand(-1, -1, Y.shape[-1]))           # :141 tf.batch_gather
+        Yg = Yg.reshape(B * pos.shape[1], -1)                                            # :142
+    else:
+        Y = layernorm(out.last_hidden, Wd["out_ln_g"], Wd["out_ln_b"])                   # CTSMA.py:80
+        Yg = Y.reshape(B * Y.shape[1], -1)                                               # :83
+    logits = Yg @ zero_pad_table(Wd["item_embs"]).t() + output_bias(Wd["output_bias"])   # :149-150 / CTSMA :89-90
+    log_probs = torch.log(torch.softmax(logits, -1) + 1e-5)                              # :155 / CTSMA :95
+    reg = l2_regularization(W, cfg, l2_reg, dtype)                                       # :158
+    ct = torch.zeros((), dtype=dtype)
+    if ct_reg != 0.:
+        st = seqs_t.to(torch.float32)                                                    # UNSCALED timestamps (Q9)
+        if cfg.model == "EasyDGL":
+            spans = torch.clamp(st[:, 1:] - st[:, :-1], 0., 100.)                        # :161 clip_by_value
+            spans = torch.cat([spans[:, :1], spans], dim=-1)                             # :162
+            spans = torch.gather(spans, 1, masked_positions.long())                      # :163
+        else:
+            spans = st[:, 1:] - st[:, :-1]                                               # CTSMA.py:100
+        spans = spans.to(dtype)
+        nm = W["mark_table"][labels.long()].to(dtype)                                    # :164 / CTSMA :101
+        posr = masked_positions.long() if cfg.model == "EasyDGL" else None
+        if h != 1:                                                                       # :166-169 / CTSMA :103-105
+            spans = spans.repeat(h, 1)
+            nm = nm.repeat(h, 1, 1)
+            if posr is not None:
+                posr = posr.repeat(h, 1)
+        for lam in out.lams:                                                             # :171 collection "LLE_PP"
+            if posr is not None:
+                lam = torch.gather(lam, 1, posr.unsqueeze(-1).expand(-1, -1, lam.shape[-1]))  # :172
+            bl = biased_likelihood(lam, nm, spans)
+            ct = ct + (ct_reg * bl / h if cfg.model == "EasyDGL" else ct_reg * bl)       # :175 / CTSMA :110
+    lab = labels.reshape(-1).long()                                                      # :178
+    weights = (lab != 0).to(dtype)                                                       # :180
+    per_example = -log_probs.gather(1, lab.unsqueeze(1)).squeeze(1)                      # :179,182 one_hot . log_probs
+    ce = (weights * per_example).sum() / (weights.sum() + 1e-5)                          # :183-185
+    res = dict(loss=ce + reg + ct, ce=ce, l2=reg, ct=ct)
+    if return_logits:
+        res["logits"] = logits
+    return res
+
+
+# ----------------------------------------------------------------------------
 # comparators (SURVEY.md section 8c)
 # ----------------------------------------------------------------------------
 def topk_set_compare(idx_test: torch.Tensor, logits64_masked: torch.Tensor, k: int, tau: float):

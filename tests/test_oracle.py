@@ -287,3 +287,37 @@ def test_topk_set_compare_excuses_only_near_ties():
     assert O.topk_set_compare(good, logits, 3, 1e-6)["exact"] == 1
     assert O.topk_set_compare(swapped, logits, 3, 1e-6)["excused"] == 1
     assert O.topk_set_compare(wrong, logits, 3, 1e-6)["bad"] == 1
+
+
+def test_train_forward_loss_restatement():
+    """EasyDGL.py:153-189 / temporal.py:317-333: the training loss against an independent numpy computation of its
+    three parts on a tiny case, and the weight-0 treatment of padded labels (EasyDGL.py:180)."""
+    import numpy as np
+    cfg, _, W = case("easy_a", batch=4)
+    tr = synth.make_train_inputs(cfg, 4, masklen=3)
+    r = O.train_forward(tr["seqs_i"], tr["seqs_t"], tr["labels"], W, cfg, tr["masked_positions"], l2_reg=1e-3, ct_reg=1e-2,
+                        return_logits=True)
+    lg = r["logits"].numpy()
+    lab = tr["labels"].reshape(-1).numpy()
+    p = np.exp(lg - lg.max(1, keepdims=True))
+    p /= p.sum(1, keepdims=True)
+    pe = -np.log(p[np.arange(len(lab)), lab] + 1e-5)
+    w = (lab != 0).astype(np.float64)
+    assert abs(float(r["ce"]) - (w * pe).sum() / (w.sum() + 1e-5)) < 1e-12
+    l2 = 1e-3 * 0.5 * sum(float((W[n].double() ** 2).sum()) for n in ("item_embs", "pos_embs", "mark_embs"))
+    assert abs(float(r["l2"]) - l2) < 1e-12
+    assert float(r["ct"]) != 0. and abs(float(r["loss"]) - float(r["ce"] + r["l2"] + r["ct"])) < 1e-12
+    # labels that are padding (0) carry weight 0: changing their logits row does not change the loss
+    lab0 = tr["labels"].clone()
+    lab0[:, 0] = 0
+    r0 = O.train_forward(tr["seqs_i"], tr["seqs_t"], lab0, W, cfg, tr["masked_positions"])
+    w0 = (lab0.reshape(-1).numpy() != 0)
+    assert abs(float(r0["ce"]) - pe[w0].sum() / (w0.sum() + 1e-5)) < 1e-9
+    # biased_likelihood: a row whose next item has no mark contributes nothing (sign(0) = 0, log(1) = 0)
+    lam = torch.rand(2, 3, 4, dtype=torch.float64) + 0.1
+    nm = torch.zeros(2, 3, 4, dtype=torch.float64)
+    nm[0, 0, 1] = 1
+    iv = torch.rand(2, 3, dtype=torch.float64)
+    bl = O.biased_likelihood(lam.clone(), nm, iv)
+    want = -(torch.log(lam[0, 0, 1]) - lam[0, 0].sum() * iv[0, 0] * .5) / 1.0
+    assert abs(float(bl) - float(want)) < 1e-12

@@ -13,187 +13,12 @@
 //   P             : 2^14 (P <= 1), folded into the softmax normaliser;  H : the scale of T (|H| <= max|T|)
 //   W1            : per tensor, in a pack built once per edgl_commit (mlp_pack_kernel)
 // Only dh = 16*k, E = 16 is instantiated; other shapes keep the TF32 kernel (attn_mma.cuh).
-#include <cuda_fp16.h>
-
-#include "attn_mma.cuh"
+#include "attn_f16_common.cuh"
 
 namespace edgl {
 namespace {
 
-__device__ __forceinline__ void mma_f16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
-      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-
-__device__ __forceinline__ uint32_t pack_h2(float e0, float e1) {  // e0 -> low half (lower k index)
-  const __half2 h = __floats2half2_rn(e0, e1);
-  return *reinterpret_cast<const uint32_t*>(&h);
-}
-
-// two (already scaled) fp32 values -> packed hi pair, packed lo pair
-__device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
-  const float h0 = __uint_as_float(__float_as_uint(x0) & 0xffffe000u);
-  const float h1 = __uint_as_float(__float_as_uint(x1) & 0xffffe000u);
-  hi = pack_h2(h0, h1);
-  lo = pack_h2(x0 - h0, x1 - h1);
-}
-
-// m >= 0: s = 2^k with m*s in [2^14, 2^15), is = 1/s (both exact; exponent clamped so neither is denormal)
-__device__ __forceinline__ void pow2_scale(float m, float& s, float& is) {
-  int e = (int)((__float_as_uint(m) >> 23) & 0xffu);
-  e = min(max(e, 15), 239);
-  s = __uint_as_float((uint32_t)(268 - e) << 23);
-  is = __uint_as_float((uint32_t)(e - 14) << 23);
-}
-
-template <int DH>
-struct F16Layout {
-  static constexpr int E = 16;
-  static constexpr int KD = DH / 16;  // k16 steps over the head dim
-  static constexpr int ND = DH / 8;   // 8-wide n tiles of a [., DH] output
-  static constexpr int NC = DH * E;   // intensity MLP width
-  static constexpr int MT = NC / 8;   // 8-column tiles of the MLP output
-  // words per K / W1^T row: KD blocks of 16 words ({hi,hi,lo,lo} x 4 lanes); = 16 (mod 32) keeps LDS.128 conflict free
-  static constexpr int SKW = KD * 16 + ((KD % 2 == 0) ? 16 : 0);
-  // constant pack (global image == shared image), byte offsets
-  static constexpr int BW_OFF = NC * SKW * 4;               // float4 per column pair {b1[c], b1[c+1], wsp[c], wsp[c+1]}
-  static constexpr int WV_OFF = BW_OFF + (NC / 2) * 16;     // int_weight [NC]
-  static constexpr int SC_OFF = WV_OFF + NC * 4;            // exp(scaling) [E]
-  static constexpr int MISC_OFF = SC_OFF + E * 4;           // {1 / scale(W1), 0, 0, 0}
-  static constexpr int PACK_BYTES = MISC_OFF + 16;
-  // K / V / T rows in shared memory: [key]{hi[DH] | lo[DH] | 16 B pad} fp16; an odd number of 16-byte chunks per
-  // row keeps the eight row addresses of an ldmatrix phase on distinct bank groups
-  static constexpr int RB = 4 * DH + 16;
-  __host__ __device__ static constexpr size_t smem_bytes(int NT) {
-    const int NB = (NT + 1) / 2, LP = NT * 8, RP = NB * 16;
-    return (size_t)PACK_BYTES + 3 * (size_t)RP * RB + (size_t)LP * 32 + (size_t)LP * 4 + 32;
-  }
-};
-
-// Built once per commit: W1 (rows 0..DH-1 of int_w, times -log2 e) transposed to [column][dim] fp16 (hi, lo)
-// fragments, the span row and bias (times -log2 e), int_weight, exp(scaling) and the W1 scale.
-template <int DH>
-__global__ void __launch_bounds__(256) mlp_pack_kernel(const float* __restrict__ int_w, const float* __restrict__ int_b,
-                                                       const float* __restrict__ int_weight,
-                                                       const float* __restrict__ int_scaling,
-                                                       unsigned char* __restrict__ pack) {
-  using LY = F16Layout<DH>;
-  constexpr int NC = LY::NC, KD = LY::KD, SKW = LY::SKW, E = LY::E;
-  __shared__ unsigned int mx;
-  if (threadIdx.x == 0) mx = 0u;
-  __syncthreads();
-  float m = 0.f;
-  for (int i = threadIdx.x; i < DH * NC; i += blockDim.x) m = fmaxf(m, fabsf(kLog2e * int_w[i]));
-  atomicMax(&mx, __float_as_uint(m));
-  __syncthreads();
-  float sw, isw;
-  pow2_scale(__uint_as_float(mx), sw, isw);
-  uint32_t* w1 = reinterpret_cast<uint32_t*>(pack);
-  for (int i = threadIdx.x; i < NC * SKW; i += blockDim.x) w1[i] = 0u;
-  __syncthreads();
-  for (int i = threadIdx.x; i < NC * KD * 4; i += blockDim.x) {
-    const int c = i / (KD * 4), ks = (i / 4) % KD, t = i % 4;
-    auto W = [&](int s) { return -kLog2e * int_w[(size_t)(ks * 16 + s) * NC + c] * sw; };
-    uint4 v;
-    split2(W(2 * t), W(2 * t + 1), v.x, v.z);          // b0: k slots 2t, 2t+1
-    split2(W(2 * t + 8), W(2 * t + 9), v.y, v.w);      // b1: k slots 2t+8, 2t+9
-    *reinterpret_cast<uint4*>(w1 + (size_t)c * SKW + ks * 16 + t * 4) = v;
-  }
-  float4* bw = reinterpret_cast<float4*>(pack + LY::BW_OFF);
-  for (int i = threadIdx.x; i < NC / 2; i += blockDim.x)
-    bw[i] = make_float4(-kLog2e * int_b[2 * i], -kLog2e * int_b[2 * i + 1], -kLog2e * int_w[(size_t)DH * NC + 2 * i],
-                        -kLog2e * int_w[(size_t)DH * NC + 2 * i + 1]);
-  float* wv = reinterpret_cast<float*>(pack + LY::WV_OFF);
-  for (int i = threadIdx.x; i < NC; i += blockDim.x) wv[i] = int_weight[i];
-  float* sc = reinterpret_cast<float*>(pack + LY::SC_OFF);
-  for (int i = threadIdx.x; i < E; i += blockDim.x) sc[i] = expf(int_scaling[i]);  // temporal.py:302
-  float* misc = reinterpret_cast<float*>(pack + LY::MISC_OFF);
-  if (threadIdx.x < 4) misc[threadIdx.x] = threadIdx.x == 0 ? isw : 0.f;
-}
-
-__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t saddr) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr));
-}
-__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], uint32_t saddr) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr));
-}
-__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src)
-               : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-
-// out[ND][4] = A[NT][.] (accumulator layout: rows g / g+8, keys nt*8 + 2t + (c&1)) times X, X staged row-major as
-// [key]{hi[DH] | lo[DH] | pad} fp16 and read with ldmatrix.trans (xs = this lane's row address for key block 0,
-// dims 0..15, hi).  Two key blocks are in flight on separate accumulators, so an accumulator is touched once per
-// 2*ND MMAs.
-template <int DH, int NT>
-__device__ __forceinline__ void pv_product16(const float (&P)[NT][4], uint32_t xs, float (&out)[DH / 8][4]) {
-  constexpr int ND = DH / 8, NB = (NT + 1) / 2, RB = F16Layout<DH>::RB;
-  float acc[2][ND][4];
-#pragma unroll
-  for (int p = 0; p < 2; ++p)
-#pragma unroll
-    for (int n = 0; n < ND; ++n) acc[p][n][0] = acc[p][n][1] = acc[p][n][2] = acc[p][n][3] = 0.f;
-#pragma unroll
-  for (int j0 = 0; j0 < NB; j0 += 2) {
-    uint32_t ah[2][4], al[2][4];
-    uint32_t xh[2][ND / 2][4], xl[2][ND / 2][4];
-#pragma unroll
-    for (int p = 0; p < 2; ++p)
-      if (j0 + p < NB) {
-        const int j = j0 + p;
-        split2(P[2 * j][0], P[2 * j][1], ah[p][0], al[p][0]);
-        split2(P[2 * j][2], P[2 * j][3], ah[p][1], al[p][1]);
-        if (2 * j + 1 < NT) {
-          split2(P[2 * j + 1][0], P[2 * j + 1][1], ah[p][2], al[p][2]);
-          split2(P[2 * j + 1][2], P[2 * j + 1][3], ah[p][3], al[p][3]);
-        } else {
-          ah[p][2] = ah[p][3] = al[p][2] = al[p][3] = 0u;
-        }
-#pragma unroll
-        for (int np = 0; np < ND / 2; ++np) {
-          ldsm_x4_trans(xh[p][np], xs + j * 16 * RB + np * 32);
-          ldsm_x4_trans(xl[p][np], xs + j * 16 * RB + np * 32 + DH * 2);
-        }
-      }
-#pragma unroll
-    for (int p = 0; p < 2; ++p)
-      if (j0 + p < NB)
-#pragma unroll
-        for (int n = 0; n < ND; ++n) mma_f16(acc[p][n], al[p], xh[p][n >> 1][(n & 1) * 2], xh[p][n >> 1][(n & 1) * 2 + 1]);
-#pragma unroll
-    for (int p = 0; p < 2; ++p)
-      if (j0 + p < NB)
-#pragma unroll
-        for (int n = 0; n < ND; ++n) mma_f16(acc[p][n], ah[p], xl[p][n >> 1][(n & 1) * 2], xl[p][n >> 1][(n & 1) * 2 + 1]);
-#pragma unroll
-    for (int p = 0; p < 2; ++p)
-      if (j0 + p < NB)
-#pragma unroll
-        for (int n = 0; n < ND; ++n) mma_f16(acc[p][n], ah[p], xh[p][n >> 1][(n & 1) * 2], xh[p][n >> 1][(n & 1) * 2 + 1]);
-  }
-#pragma unroll
-  for (int n = 0; n < ND; ++n)
-#pragma unroll
-    for (int c = 0; c < 4; ++c) out[n][c] = acc[0][n][c] + acc[1][n][c];
-}
-
-__device__ __forceinline__ float absmax4(float m, const float4& v) {
-  return fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
-}
-// 4 consecutive dims of one key -> 8 bytes of hi and 8 bytes of lo in the key's row
-__device__ __forceinline__ void put4(unsigned char* row, int dim0, int DH2, const float4& v, float s) {
-  uint2 hi, lo;
-  split2(v.x * s, v.y * s, hi.x, lo.x);
-  split2(v.z * s, v.w * s, hi.y, lo.y);
-  *reinterpret_cast<uint2*>(row + dim0 * 2) = hi;
-  *reinterpret_cast<uint2*>(row + DH2 + dim0 * 2) = lo;
-}
+using namespace f16c;
 
 // NT = number of 8-key tiles held in registers (L <= 8*NT); HPC heads are processed by one CTA in turn.
 // MAXREG bounds the registers per thread and so the CTAs per SM (7 warps/CTA at L = 100: 128 -> 2, 80 -> 3, 72 -> 4).
@@ -407,9 +232,11 @@ __global__ void __maxnreg__(MAXREG) attention_f16_kernel(AttnArgs a, int hpc) {
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) {
         const float2 kmv = *reinterpret_cast<const float2*>(km + nt * 8 + 2 * t);
+        upk2(mul2(pk2(P[nt][0], P[nt][1]), pk2(sca, sca)), P[nt][0], P[nt][1]);
+        upk2(mul2(pk2(P[nt][2], P[nt][3]), pk2(scb, scb)), P[nt][2], P[nt][3]);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          float s = fminf(P[nt][c] * ((c < 2) ? sca : scb), (c & 1) ? kmv.y : kmv.x);
+          float s = fminf(P[nt][c], (c & 1) ? kmv.y : kmv.x);
           if (a.causal) {
             const int col = nt * 8 + 2 * t + (c & 1);
             if (col > ((c < 2) ? qa : qb)) s = fminf(s, kFillMma);  // temporal.py:362-367
@@ -422,15 +249,23 @@ __global__ void __maxnreg__(MAXREG) attention_f16_kernel(AttnArgs a, int hpc) {
       ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, 2));
       mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, 1));
       mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, 2));
-      float la = 0.f, lb = 0.f;
+      float la, lb;
+      {
+        f32x2 la2 = pk2(0.f, 0.f), lb2 = la2;
+        const f32x2 ma2 = pk2(ma, ma), mb2 = pk2(mb, mb);
 #pragma unroll
-      for (int nt = 0; nt < NT; ++nt) {
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const float p = ex2_approx(P[nt][c] - ((c < 2) ? ma : mb));
-          P[nt][c] = p;
-          if (c < 2) la += p; else lb += p;
+        for (int nt = 0; nt < NT; ++nt) {
+          float d0, d1, d2, d3;
+          upk2(sub2(pk2(P[nt][0], P[nt][1]), ma2), d0, d1);
+          upk2(sub2(pk2(P[nt][2], P[nt][3]), mb2), d2, d3);
+          P[nt][0] = ex2_approx(d0); P[nt][1] = ex2_approx(d1);
+          P[nt][2] = ex2_approx(d2); P[nt][3] = ex2_approx(d3);
+          la2 = add2(la2, pk2(P[nt][0], P[nt][1]));
+          lb2 = add2(lb2, pk2(P[nt][2], P[nt][3]));
         }
+        float l0, l1;
+        upk2(la2, l0, l1); la = l0 + l1;
+        upk2(lb2, l0, l1); lb = l0 + l1;
       }
       la += __shfl_xor_sync(0xffffffffu, la, 1);
       la += __shfl_xor_sync(0xffffffffu, la, 2);
@@ -440,7 +275,8 @@ __global__ void __maxnreg__(MAXREG) attention_f16_kernel(AttnArgs a, int hpc) {
       const float ia = __frcp_rn(la) * 16384.f, ib = __frcp_rn(lb) * 16384.f;
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) {
-        P[nt][0] *= ia; P[nt][1] *= ia; P[nt][2] *= ib; P[nt][3] *= ib;
+        upk2(mul2(pk2(P[nt][0], P[nt][1]), pk2(ia, ia)), P[nt][0], P[nt][1]);
+        upk2(mul2(pk2(P[nt][2], P[nt][3]), pk2(ib, ib)), P[nt][2], P[nt][3]);
       }
       // ---- H = P T : accumulator = H * 2^14 * scale(T); |H * scale(T)| < 2^15 because rows of P sum to 1
       float H[ND][4];
@@ -467,7 +303,9 @@ __global__ void __maxnreg__(MAXREG) attention_f16_kernel(AttnArgs a, int hpc) {
       for (int i = 0; i < 4; ++i) va[i] = vb[i] = 0.f;
 #pragma unroll 1
       for (int eg = 0; eg < E / 4; ++eg) {
-        float pa[4] = {0.f, 0.f, 0.f, 0.f}, pb[4] = {0.f, 0.f, 0.f, 0.f};
+        f32x2 pa2[4], pb2[4];  // two-lane partial sums (even / odd columns) of the four events, rows a / b
+#pragma unroll
+        for (int i = 0; i < 4; ++i) pa2[i] = pb2[i] = pk2(0.f, 0.f);
         const uint32_t* w1g = W1t + (size_t)(eg * 4 * ND * 8 + g) * SKW + t * 4;
         const float4* bwg = bw + eg * 4 * ND * 4 + t;
         const float* wvg = wv + eg * 4 * ND * 8 + 2 * t;
@@ -494,14 +332,24 @@ __global__ void __maxnreg__(MAXREG) attention_f16_kernel(AttnArgs a, int hpc) {
             const int tl = tq * 4 + j;         // tile inside the group; its event is tl / ND
             const float4 bb = bwg[tl * 4];     // {b1[c0], b1[c0+1], wsp[c0], wsp[c0+1]}, c0 = tile*8 + 2t
             const float2 we = *reinterpret_cast<const float2*>(wvg + tl * 8);
-            const float z0 = fmaf(z[j][0], zscale, fmaf(spa, bb.z, bb.x)), z1 = fmaf(z[j][1], zscale, fmaf(spa, bb.w, bb.y));
-            const float z2 = fmaf(z[j][2], zscale, fmaf(spb, bb.z, bb.x)), z3 = fmaf(z[j][3], zscale, fmaf(spb, bb.w, bb.y));
+            const f32x2 b2 = pk2(bb.x, bb.y), w2 = pk2(bb.z, bb.w), zs2 = pk2(zscale, zscale), we2 = pk2(we.x, we.y);
+            float z0, z1, z2, z3;
+            upk2(fma2(pk2(z[j][0], z[j][1]), zs2, fma2(pk2(spa, spa), w2, b2)), z0, z1);
+            upk2(fma2(pk2(z[j][2], z[j][3]), zs2, fma2(pk2(spb, spb), w2, b2)), z2, z3);
             // z* hold -z*log2(e): sigmoid = 1 / (1 + 2^(z*))   (tf.nn.sigmoid, temporal.py:290)
-            pa[tl / ND] = fmaf(rcp_approx(1.f + ex2_approx(z0)), we.x, pa[tl / ND]);
-            pa[tl / ND] = fmaf(rcp_approx(1.f + ex2_approx(z1)), we.y, pa[tl / ND]);
-            pb[tl / ND] = fmaf(rcp_approx(1.f + ex2_approx(z2)), we.x, pb[tl / ND]);
-            pb[tl / ND] = fmaf(rcp_approx(1.f + ex2_approx(z3)), we.y, pb[tl / ND]);
+            float a0, a1, a2, a3;
+            upk2(add2(pk2(ex2_approx(z0), ex2_approx(z1)), pk2(1.f, 1.f)), a0, a1);
+            upk2(add2(pk2(ex2_approx(z2), ex2_approx(z3)), pk2(1.f, 1.f)), a2, a3);
+            pa2[tl / ND] = fma2(pk2(rcp_approx(a0), rcp_approx(a1)), we2, pa2[tl / ND]);
+            pb2[tl / ND] = fma2(pk2(rcp_approx(a2), rcp_approx(a3)), we2, pb2[tl / ND]);
           }
+        }
+        float pa[4], pb[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float l0, l1;
+          upk2(pa2[i], l0, l1); pa[i] = l0 + l1;
+          upk2(pb2[i], l0, l1); pb[i] = l0 + l1;
         }
         // 4x4 transpose-reduce over the quad: lane t ends with the sum over lanes of p[t]
         const bool odd = (t & 1) != 0, up = (t & 2) != 0;
@@ -584,11 +432,12 @@ __global__ void __maxnreg__(MAXREG) attention_f16_kernel(AttnArgs a, int hpc) {
             for (int c = 0; c < 4; ++c) {
               const int col = (n0 + j) * 8 + 2 * t + (c & 1);
               const int qr = (c < 2) ? qa : qb;
-              const float gg = (a.diag_one && col == qr) ? ((c < 2) ? sla : slb) : G[j][c];
-              const float v = P[n0 + j][c] * gg;
-              P[n0 + j][c] = v;
-              if (c < 2) ga = fmaxf(ga, fabsf(v)); else gb = fmaxf(gb, fabsf(v));
+              G[j][c] = (a.diag_one && col == qr) ? ((c < 2) ? sla : slb) : G[j][c];
             }
+            upk2(mul2(pk2(P[n0 + j][0], P[n0 + j][1]), pk2(G[j][0], G[j][1])), P[n0 + j][0], P[n0 + j][1]);
+            upk2(mul2(pk2(P[n0 + j][2], P[n0 + j][3]), pk2(G[j][2], G[j][3])), P[n0 + j][2], P[n0 + j][3]);
+            ga = fmaxf(ga, fmaxf(fabsf(P[n0 + j][0]), fabsf(P[n0 + j][1])));
+            gb = fmaxf(gb, fmaxf(fabsf(P[n0 + j][2]), fabsf(P[n0 + j][3])));
           }
       }
       ga = fmaxf(ga, __shfl_xor_sync(0xffffffffu, ga, 1));
@@ -600,7 +449,8 @@ __global__ void __maxnreg__(MAXREG) attention_f16_kernel(AttnArgs a, int hpc) {
       pow2_scale(gb, sgb, isgb);
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) {
-        P[nt][0] *= sga; P[nt][1] *= sga; P[nt][2] *= sgb; P[nt][3] *= sgb;
+        upk2(mul2(pk2(P[nt][0], P[nt][1]), pk2(sga, sga)), P[nt][0], P[nt][1]);
+        upk2(mul2(pk2(P[nt][2], P[nt][3]), pk2(sgb, sgb)), P[nt][2], P[nt][3]);
       }
       // ---- O = (G o P) V : accumulator = O * 2^14 * scale(lam row) * scale(G o P row) * scale(V)
       float O[ND][4];

@@ -502,13 +502,17 @@ int launch_f16_t(const AttnArgs& a, int hpc, cudaStream_t st) {
 size_t attention_f16_pack_bytes(int dh, int E) {
   if (E != 16) return 0;
   if (dh == 16) return F16Layout<16>::PACK_BYTES;
+  if (dh == 32) return F16Layout<32>::PACK_BYTES;  // attn_f16_long.cu
   return 0;
 }
 
 int launch_attention_f16_pack(const float* int_w, const float* int_b, const float* int_weight, const float* int_scaling,
                               int dh, int E, void* pack, cudaStream_t st) {
   EDGL_REQUIRE(attention_f16_pack_bytes(dh, E) != 0, "attention pack: dh=%d E=%d not supported", dh, E);
-  mlp_pack_kernel<16><<<1, 256, 0, st>>>(int_w, int_b, int_weight, int_scaling, reinterpret_cast<unsigned char*>(pack));
+  if (dh == 16)
+    mlp_pack_kernel<16><<<1, 256, 0, st>>>(int_w, int_b, int_weight, int_scaling, reinterpret_cast<unsigned char*>(pack));
+  else
+    mlp_pack_kernel<32><<<1, 256, 0, st>>>(int_w, int_b, int_weight, int_scaling, reinterpret_cast<unsigned char*>(pack));
   EDGL_LAUNCH_CHECK();
   return 0;
 }
@@ -516,6 +520,9 @@ int launch_attention_f16_pack(const float* int_w, const float* int_b, const floa
 // returns 0 = launched, 1 = shape not covered, <0 = error
 int launch_attention_f16(const AttnArgs& a, cudaStream_t st) {
   const int dh = a.d / a.h;
+  // long sequences / head dim 32: the key-streaming two-pass kernel (attn_f16_long.cu); EDGL_ATTN_LONG=1 forces it
+  static const bool force_long = getenv("EDGL_ATTN_LONG") != nullptr;
+  if (force_long || dh == 32 || (dh == 16 && a.L > 208)) return launch_attention_f16_long(a, st);
   if (dh != 16 || a.E != 16 || !a.mlp_pack || a.L > 208) return 1;
   if (reinterpret_cast<uintptr_t>(a.marks) & 15) return 1;  // mark rows are read as 16-byte words
   static const int hpc_env = [] {

@@ -165,6 +165,8 @@ struct AttnArgs {
 int launch_attention(const AttnArgs& a, cudaStream_t st);
 // scaled 3xFP16 mma.sync kernel (attn_f16.cu): 0 = launched, 1 = shape not covered, <0 = error
 int launch_attention_f16(const AttnArgs& a, cudaStream_t st);
+// key-streaming two-pass variant (attn_f16_long.cu): dh in {16, 32}, E = 16, any L
+int launch_attention_f16_long(const AttnArgs& a, cudaStream_t st);
 size_t attention_f16_pack_bytes(int dh, int E);  // 0 if the shape is not covered
 int launch_attention_f16_pack(const float* int_w, const float* int_b, const float* int_weight, const float* int_scaling,
                               int dh, int E, void* pack, cudaStream_t st);

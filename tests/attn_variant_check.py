@@ -87,6 +87,11 @@ def main():
         ("C2", 3, False, dict(q=2.0 ** 30, k=2.0 ** -30, v=2.0 ** -40, t=2.0 ** 6, mlp=2.0 ** -6), {}),
         ("C3", 3, True, dict(q=37.0, k=1.0 / 37.0, v=1.0e-6, t=3.0e3, mlp=1.0 / 3.0e3), {}),
         ("C2", 3, False, unit, dict(seqslen=119)), ("C2", 2, False, unit, dict(seqslen=199)),
+        # head dim 32, L = 512 (C5's shape; attn_f16_long.cu by default), also over a wide operand range, and a
+        # length that is neither a multiple of the 64-key chunk nor of the 256-row query block
+        ("C5", 2, False, unit, dict(num_items=3000)),
+        ("C5", 1, False, dict(q=2.0 ** -20, k=2.0 ** 20, v=2.0 ** 12, t=2.0 ** -9, mlp=2.0 ** 9), dict(num_items=3000)),
+        ("C5", 2, False, unit, dict(num_items=3000, seqslen=300)),
     ]
     for name, batch, causal, scales, over in layer_runs:
         r = layer_case(name, batch, causal, scales, **over)

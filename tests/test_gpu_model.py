@@ -216,7 +216,7 @@ def test_alternative_attention_kernels_agree(mode):
     assert "SIMT_OK" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
 
 
-@pytest.mark.parametrize("mode", ["mma", "f16"])
+@pytest.mark.parametrize("mode", ["mma", "f16", "f16-long"])
 def test_attention_variant_layers(mode):
     """Layer-level (BiMAU / MAU) and model-level parity of one tensor-core attention kernel at fp32-level
     tolerance (2e-5 of max|ref| vs the fp64 oracle), with Q/K/V/T/MLP operands rescaled by up to 2^+-40: the
@@ -224,7 +224,9 @@ def test_attention_variant_layers(mode):
     import subprocess
     import sys
     script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "attn_variant_check.py")
-    env = dict(os.environ, EDGL_ATTN=mode)
+    env = dict(os.environ, EDGL_ATTN=mode.split("-")[0])
+    if mode.endswith("-long"):  # the key-streaming two-pass kernel (attn_f16_long.cu) for every shape
+        env["EDGL_ATTN_LONG"] = "1"
     res = subprocess.run([sys.executable, script], env=env, capture_output=True, text=True, timeout=280)
     assert "VARIANT_OK" in res.stdout, res.stdout[-3000:] + res.stderr[-2000:]
 

@@ -65,6 +65,7 @@ struct edgl_handle {
   float* tscale = nullptr;
   uint8_t* mark8 = nullptr;
   int* flag = nullptr;
+  int* topk_redo = nullptr;  // device flag of the fused logits + top-K path: a row needs the materialised fallback
   unsigned int* p2p_counter = nullptr;  // grid-done counters of the fused-exchange kernels (zero-initialised)
   float* bias_full = nullptr;  // [N1] = concat([-1000], output_bias)  (Base.py:110)
   float* table_lo = nullptr;   // [c1-c0, d] tf32 lo part of the owned item-table rows (logits GEMM), or null
@@ -479,19 +480,60 @@ int train_encode(edgl_handle* h, const int64_t* ids, const float* ts, int B, con
 }
 
 // logits[r0:r0+rc, c0:c1] = y @ table[c0:c1]^T + bias   (EasyDGL.py:149-150 / CTSMA.py:89-90, Base.py:106-110)
-int logits_rows(edgl_handle* h, const float* y, int ldy, long long rc, float* out, int ldo, cudaStream_t st) {
+// ncols > 0: only the first ncols columns of the shard; flt: candidate filter instead of the store (tensor-core kernel);
+// run_if: predicated launch
+bool logits_use_f16(const edgl_handle* h, const float* y) {
+  return h->f16_gemm && (h->f16_mask & 32) && y == h->y && h->mt16.count("table");
+}
+int logits_rows(edgl_handle* h, const float* y, int ldy, long long rc, float* out, int ldo, cudaStream_t st,
+                int ncols = 0, const TopkFilter* flt = nullptr, const int* run_if = nullptr) {
   GemmArgs g;
   g.A = y; g.lda = ldy;
   g.W = F(h->mt, "item_embs") + h->c0 * h->d; g.ldw = h->d; g.w_is_nk = true;
   g.Wlo = h->table_lo;
-  if (h->f16_gemm && (h->f16_mask & 32) && y == h->y && h->mt16.count("table")) {  // the local encoder's y: its maximum is in AMAX_Y
+  if (logits_use_f16(h, y) && !flt && !run_if) {  // the local encoder's y: its maximum is in AMAX_Y
     g.W16 = h->mt16.at("table");
     g.a_amax = h->amax + AMAX_Y;
   }
   g.zero_wrow0 = (h->c0 == 0);  // zero_pad=True: row 0 of the tied table is zeros (coding.py:56-57)
-  g.C = out; g.ldc = ldo; g.M = (int)rc; g.N = (int)(h->c1 - h->c0); g.K = h->d;
+  g.C = out; g.ldc = ldo; g.M = (int)rc; g.N = ncols > 0 ? ncols : (int)(h->c1 - h->c0); g.K = h->d;
   g.bias = h->bias_full + h->c0;
+  if (flt) g.flt = *flt;
+  g.run_if = run_if;
   return launch_gemm(g, st);
+}
+
+// Fused logits + seen-mask + top-K of one chunk of rows WITHOUT materialising [rows, Ns] (EasyDGL.py:149-150,
+// Base.py:156-181; SURVEY 7.6 / 8e "top-K in the GEMM epilogue"):
+//   1. logits of a column SAMPLE (the first ns columns of the shard), seen-mask, its K-th largest value per row =
+//      thr[row]: at least K unmasked logits of the row are >= thr, so thr is a lower bound of the row's K-th largest;
+//   2. the logits GEMM over all columns with the candidate-filter epilogue: (value, column) of everything >= thr;
+//   3. exact top-K of the unmasked candidates (topk_select_kernel).
+// Same kernel and same accumulation order as the materialised path, so the selected values are bit-identical to it.
+// A row with too many candidates (ties, a constant row, a sample that under-estimates) or too few raises a device
+// flag and the materialised path - launched unconditionally, predicated on that flag - recomputes the chunk.
+bool topk_fused_ok(const edgl_handle* h, const float* y, long long Ns, long long ldw, int* ns_out, int* cap_out) {
+  // Measured (one B200, B = 4096 / 1024 / 2048 rows): C5's 1 000 001 columns 12.1 -> 7.9 ms (the [B, N1] round trip
+  // and the 4 re-streams of the table are gone), C4's 100 001 columns 0.42 -> 0.46 ms and C2's 18 001 columns
+  // 0.27 -> 0.46 ms (two more per-row kernels and seven more launches than the materialised path: fixed costs that
+  // short rows do not amortise).  So the fused path is the default for shards of >= 200 000 columns;
+  // EDGL_TOPK_FUSE=1 forces it for every shard it supports (>= 8192 columns), =0 turns it off;
+  // EDGL_TOPK_SAMPLE=n sets the sample width.  Read per call: test switches.
+  const char* fe = getenv("EDGL_TOPK_FUSE");
+  const bool off = (fe && fe[0] == '0') || (!(fe && fe[0] == '1') && Ns < 200000);
+  const char* se = getenv("EDGL_TOPK_SAMPLE");
+  const int ns_env = se ? atoi(se) : 0;
+  static const bool simt = [] { const char* e = getenv("EDGL_GEMM"); return e && e[0] == 's'; }();
+  if (off || simt || logits_use_f16(h, y) || h->K > 256 || (h->d % 4) != 0) return false;
+  long long ns = ns_env > 0 ? ns_env : ((Ns / 16 + 255) / 256) * 256;
+  if (ns < 2048) ns = 2048;
+  if (ns * 4 > Ns || ns < 8 * h->K) return false;  // short rows: the sample would be most of the row
+  int cap = 4096;
+  if (ns + 2 * cap + 1 + 2 * h->K > ldw) cap = 2048;
+  if (ns + 2 * cap + 1 + 2 * h->K > ldw) return false;
+  *ns_out = (int)ns;
+  *cap_out = cap;
+  return true;
 }
 
 int logits_topk(edgl_handle* h, const float* y, int ldy, const int64_t* seen, int seen_len, long long seen_stride,
@@ -502,13 +544,44 @@ int logits_topk(edgl_handle* h, const float* y, int ldy, const int64_t* seen, in
   if (seen_stride == 0) seen_stride = seen_len;
   const int Ns = (int)(h->c1 - h->c0);
   const int ldw = (Ns + 3) & ~3;  // padded pitch: vector stores in the GEMM epilogue
+  int ns = 0, cap = 0;
+  const bool fused = !p2p && topk_fused_ok(h, y, Ns, ldw, &ns, &cap);
   for (long long r0 = 0; r0 < Bt; r0 += h->ws_rows) {
     const long long rc = (Bt - r0 < h->ws_rows) ? (Bt - r0) : h->ws_rows;
+    const int64_t* seen_r = seen ? seen + r0 * seen_stride : nullptr;
+    const int* run_if = nullptr;
+    if (fused) {
+      // workspace of the chunk, carved out of logits_ws: sample logits | candidates | counters | sample top-K
+      float* samp = h->logits_ws;
+      unsigned long long* cand = reinterpret_cast<unsigned long long*>(samp + rc * ns);
+      unsigned int* cnt = reinterpret_cast<unsigned int*>(cand + rc * cap);
+      float* tval = reinterpret_cast<float*>(cnt + rc);
+      int32_t* tidx = reinterpret_cast<int32_t*>(tval + rc * h->K);
+      mark(h, ST_LOGITS_GEMM, st);
+      EDGL_TRY(logits_rows(h, y + r0 * ldy, ldy, rc, samp, ns, st, ns));
+      if (seen) {
+        mark(h, ST_MASK_SEEN, st);
+        EDGL_TRY(launch_mask_seen(samp, ns, (int)rc, seen_r, seen_len, seen_stride, h->c0, h->c0 + ns, st));
+      }
+      mark(h, ST_TOPK, st);
+      EDGL_TRY(launch_topk(samp, ns, (int)rc, ns, h->K, 0, h->K, tidx, tval, st));
+      EDGL_CUDA(cudaMemsetAsync(cnt, 0, (size_t)rc * sizeof(unsigned int), st));
+      EDGL_CUDA(cudaMemsetAsync(h->topk_redo, 0, sizeof(int), st));
+      mark(h, ST_LOGITS_GEMM, st);
+      TopkFilter flt;
+      flt.thr = tval + (h->K - 1); flt.thr_stride = h->K;
+      flt.cand = cand; flt.cap = cap; flt.cnt = cnt;
+      EDGL_TRY(logits_rows(h, y + r0 * ldy, ldy, rc, nullptr, 0, st, 0, &flt));
+      mark(h, ST_TOPK, st);
+      EDGL_TRY(launch_topk_select(cand, cnt, cap, (int)rc, h->K, (int)h->c0, seen_r, seen_len, seen_stride, h->c0, h->c1,
+                                  ostride, idx + r0 * ostride, val + r0 * ostride, h->topk_redo, st));
+      run_if = h->topk_redo;  // the launches below do nothing unless a row asked for the materialised path
+    }
     mark(h, ST_LOGITS_GEMM, st);
-    EDGL_TRY(logits_rows(h, y + r0 * ldy, ldy, rc, h->logits_ws, ldw, st));
+    EDGL_TRY(logits_rows(h, y + r0 * ldy, ldy, rc, h->logits_ws, ldw, st, 0, nullptr, run_if));
     if (seen) {
       mark(h, ST_MASK_SEEN, st);
-      EDGL_TRY(launch_mask_seen(h->logits_ws, ldw, (int)rc, seen + r0 * seen_stride, seen_len, seen_stride, h->c0, h->c1, st));
+      EDGL_TRY(launch_mask_seen(h->logits_ws, ldw, (int)rc, seen_r, seen_len, seen_stride, h->c0, h->c1, st, run_if));
     }
     mark(h, ST_TOPK, st);
     if (p2p) {
@@ -518,7 +591,7 @@ int logits_topk(edgl_handle* h, const float* y, int ldy, const int64_t* seen, in
       EDGL_TRY(launch_topk(h->logits_ws, ldw, (int)rc, Ns, h->K, (int)h->c0, 0, nullptr, nullptr, st, &pp));
     } else {
       EDGL_TRY(launch_topk(h->logits_ws, ldw, (int)rc, Ns, h->K, (int)h->c0, ostride, idx + r0 * ostride,
-                           val + r0 * ostride, st));
+                           val + r0 * ostride, st, nullptr, run_if));
     }
   }
   mark(h, ST_END, st);
@@ -580,6 +653,7 @@ int edgl_create(const edgl_config* cfg, edgl_handle** out) {
   EDGL_ALLOC(h->tscale, d / 2);
   EDGL_ALLOC(h->mark8, (long long)cfg->mark_rows * h->E);
   EDGL_ALLOC(h->flag, 1);
+  EDGL_ALLOC(h->topk_redo, 1);
   EDGL_ALLOC(h->p2p_counter, 4);
   if (!rc && cudaMemset(h->p2p_counter, 0, 4 * sizeof(unsigned int)) != cudaSuccess) rc = set_error(EDGL_ECUDA, "cudaMemset failed");
   EDGL_ALLOC(h->bias_full, h->N1);

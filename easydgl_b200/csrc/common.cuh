@@ -79,6 +79,29 @@ struct LnEpi {
   bool any() const { return a_rs || r_rs || stats || last_only; }
 };
 int ln_stats_parts(int N);  // number of partials per row the tensor-core GEMM writes for N columns
+
+// order-preserving unsigned keys of fp32 values and the 64-bit (key, ~index) words the ranking kernels sort:
+// descending order of the word = (value descending, index ascending), tf.nn.top_k's order (Base.py:181)
+__device__ __forceinline__ uint32_t f2key(float f) {
+  uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key2f(uint32_t k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+__device__ __forceinline__ unsigned long long compose(uint32_t key, uint32_t idx) {
+  return ((unsigned long long)key << 32) | (unsigned long long)(0xffffffffu - idx);
+}
+
+// Top-K candidate filter in the epilogue of the logits GEMM (gemm_tc.cu; api.cu logits_topk): instead of storing
+// C, every value >= thr[row] - a lower bound of the row's K-th largest unmasked logit, taken from a column sample -
+// is appended to the row's candidate list as a (key, column) word.  cnt[row] counts every hit, also those beyond
+// `cap` (the caller detects the overflow and falls back to the materialised path).
+struct TopkFilter {
+  const float* thr = nullptr; long long thr_stride = 0;
+  unsigned long long* cand = nullptr; int cap = 0;  // [M][cap]
+  unsigned int* cnt = nullptr;                      // [M], zeroed by the caller
+};
 // (mean, rstd)[b] from the row partials of B sequences of L rows x C columns; optionally y[b] = LN(x_last[b]) with
 // x_last [B, C] (the stored last rows), gamma, beta
 int launch_ln_finalize(const float2* parts, int nparts, int B, int L, int C, float2* rs, const float* x_last,
@@ -104,6 +127,8 @@ struct GemmArgs {
   int act = ACT_NONE;
   bool zero_wrow0 = false;  // w_is_nk only: treat W row 0 (= output column 0) as all-zero (zero_pad table)
   LnEpi ln;                 // tensor-core path only (3xTF32 kernel): fused LayerNorm pieces, see above
+  TopkFilter flt;           // tensor-core path only (3xTF32 kernel): candidate filter instead of the store of C
+  const int* run_if = nullptr;  // device flag or null: the kernel does nothing when *run_if == 0 (fallback launches)
 };
 int launch_gemm(const GemmArgs& a, cudaStream_t st);
 bool gemm_tc_supported(const GemmArgs& a);
@@ -199,7 +224,7 @@ int launch_reduce(const float* x, long long n, int squares, double scale, double
 int launch_loss_combine(const double* acc, int num_blocks, double ct_scale, float* loss_out, cudaStream_t st);
 
 int launch_mask_seen(float* logits, int ld, int B, const int64_t* ids, int seen_len, long long seen_stride,
-                     long long col0, long long col1, cudaStream_t st);
+                     long long col0, long long col1, cudaStream_t st, const int* run_if = nullptr);
 // Fused candidate exchange over peer memory (multi-GPU): when `dest` is set the top-K kernel writes row R's
 // candidates into the receive buffer of rank R / rows_per_dest and, after the last launch of a step, raises
 // `epoch` in every peer's flag array.
@@ -211,7 +236,12 @@ struct TopkP2P {
   uint32_t epoch;
 };
 int launch_topk(const float* logits, int ld, int B, int N, int K, int col_offset, long long out_stride, int32_t* idx,
-                float* val, cudaStream_t st, const TopkP2P* p2p = nullptr);
+                float* val, cudaStream_t st, const TopkP2P* p2p = nullptr, const int* run_if = nullptr);
+// exact top-K of the candidate lists a TopkFilter epilogue produced (ids of the row's own sequence dropped: seen-mask,
+// Base.py:156-163); rows whose list overflowed `cap` or holds fewer than K unmasked entries raise *redo
+int launch_topk_select(const unsigned long long* cand, const unsigned int* cnt, int cap, int B, int K, int col_offset,
+                       const int64_t* seen, int seen_len, long long seen_stride, long long col0, long long col1,
+                       long long out_stride, int32_t* idx, float* val, int* redo, cudaStream_t st);
 int launch_put_rows(const float* y, long long ldy, const int64_t* ids, int L, int d, int B, const long long* peer_rows,
                     int G, int rank, const long long* peer_flags, uint32_t epoch, unsigned int* counter,
                     cudaStream_t st);

@@ -231,6 +231,10 @@ int launch_gemm(const GemmArgs& a, cudaStream_t st) {
     const char* e = getenv("EDGL_GEMM");
     return e && e[0] == 's';
   }();
+  if (a.flt.cand || a.run_if) {  // candidate filter / predicated launch: 3xTF32 tensor-core kernel only
+    EDGL_REQUIRE(gemm_tc_supported(a), "gemm: the top-K filter epilogue needs the tensor-core path");
+    return launch_gemm_tc(a, st);
+  }
   if (a.ln.any()) {  // fused LayerNorm pieces exist in the 3xTF32 tensor-core kernel only (callers check EDGL_GEMM)
     EDGL_REQUIRE(gemm_tc_supported(a), "gemm: a fused-LayerNorm dense layer needs the tensor-core path");
     return launch_gemm_tc(a, st);

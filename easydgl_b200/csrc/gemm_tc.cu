@@ -79,6 +79,8 @@ struct Params {
   int col0_bias_only;  // tied zero-padded table: column 0 is exactly the bias (coding.py:56-57)
   int ntn, num_tiles, kblocks;
   LnEpi ln;        // fused LayerNorm pieces of the epilogue (common.cuh); all null = off
+  TopkFilter flt;  // top-K candidate filter instead of the store (LN_FILT instantiation only)
+  const int* run_if;  // device flag or null: return at once when *run_if == 0
   int epi_direct;  // epilogue stores rows straight from TMEM fragments (no shared-memory transpose)
   int has_blo;  // W_lo = W - tf32(W) is pre-computed in global memory (weights are constant after commit): TMA brings
                 // it in like W and the splitter warps only split the activations
@@ -111,6 +113,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   uint64_t* tempty = tfull + 2;     // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
+  if (p.run_if && *p.run_if == 0) return;  // predicated fallback launch (block-uniform; nothing is allocated yet)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   auto stA = [&](int s) { return base + s * SM::STAGE; };
   auto stAlo = [&](int s) { return base + s * SM::STAGE + SM::A_BYTES; };
@@ -397,6 +400,8 @@ int launch_gemm_tc(const GemmArgs& a, cudaStream_t st) {
   }();
   p.epi_direct = epi_mode == 'd' ? 1 : epi_mode == 's' ? 0 : (a.R == nullptr && a.pbias == nullptr) ? 1 : 0;
   p.ln = a.ln;
+  p.flt = a.flt;
+  p.run_if = a.run_if;
   int lnf = 0;
   if (a.ln.any()) {
     // the fused LayerNorm pieces live in the staged fast path of the epilogue (and in the splitter warps) only
@@ -428,6 +433,14 @@ int launch_gemm_tc(const GemmArgs& a, cudaStream_t st) {
     auto kern = gemm_tc_kernel<BNV, ACTV, LNV>;                                                                \
     EDGL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BNV>::BYTES));      \
     kern<<<grid, NTHREADS, Smem<BNV>::BYTES, st>>>(mapA, mapB, mapBlo, p);                                     \
+  }
+  if (a.flt.cand) {  // candidate filter of the logits layer: bias only
+    EDGL_REQUIRE(lnf == 0 && a.act == ACT_NONE && !a.R && !a.pbias && a.flt.thr && a.flt.cnt && a.flt.cap > 0,
+                 "gemm_tc: the top-K filter epilogue takes a plain bias layer");
+    if (bn == 256) EDGL_TC_LAUNCH_L(256, ACT_NONE, LN_FILT)
+    else EDGL_TC_LAUNCH_L(128, ACT_NONE, LN_FILT)
+    EDGL_LAUNCH_CHECK();
+    return 0;
   }
   // the fused-LayerNorm combinations the EasyDGL block tail uses (api.cu): attention-out (statistics), FF1 (A is a
   // LayerNorm; GELU), FF2 (residual is a LayerNorm; statistics), transform (A is a LayerNorm; GELU; statistics; last rows)

@@ -124,7 +124,9 @@ __device__ __forceinline__ float gelu_erf_exact(float x) {
 // LNF (bit mask, gemm_tc.cu only): fused LayerNorm pieces of LnEpi (common.cuh) - LN_RES: the residual rows are
 // LayerNorm(R); LN_STATS: per-row partial sums of the stored values; LN_LAST: store only the last row of every
 // sequence.  (LN_A, the normalisation of the A operand, lives in the splitter warps.)
-constexpr int LN_A = 1, LN_RES = 2, LN_STATS = 4, LN_LAST = 8;
+// LN_FILT (same bit mask, not a LayerNorm piece): the epilogue stores nothing and appends the values that pass the
+// row's threshold to the top-K candidate lists of p.flt (TopkFilter, common.cuh).
+constexpr int LN_A = 1, LN_RES = 2, LN_STATS = 4, LN_LAST = 8, LN_FILT = 16;
 
 template <int BN, int ACT, bool SCALED, int LNF = 0, class P>
 __device__ __forceinline__ void epilogue_tile(const P& p, uint32_t tmem_acc, int m0, int n0, int q, int part, int lane,
@@ -141,6 +143,52 @@ __device__ __forceinline__ void epilogue_tile(const P& p, uint32_t tmem_acc, int
     if constexpr (SCALED) x *= inv;
     return x;
   };
+  if constexpr ((LNF & LN_FILT) != 0) {
+    // ---- top-K candidate filter (logits layer: bias only).  tcgen05.ld hands this thread 16 consecutive columns of
+    // ONE row; the value is formed exactly as the storing paths form it (accumulator, column 0 = bias, + bias), so a
+    // candidate carries the bits the materialised logits would.  One atomic per (row, 16 columns) that has hits.
+    const int row = m0 + q * 32 + lane;
+    const bool row_ok = row < p.M;
+    const float thr = row_ok ? p.flt.thr[(size_t)row * p.flt.thr_stride] : INFINITY;
+    const bool bias_al = p.bias && ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
+#pragma unroll 1
+    for (int c0 = part * CW; c0 < BN; c0 += EPI_PARTS * CW) {
+      uint32_t r[CW];
+      tmem_ld16(tmem_acc + c0 + ((uint32_t)(q * 32) << 16), r);
+      const int colb = n0 + c0;
+      if (colb >= p.N) continue;  // warp-uniform
+      float v[CW];
+      if (bias_al && colb + CW <= p.N) {
+#pragma unroll
+        for (int j = 0; j < CW / 4; ++j) {
+          const float4 b4 = *reinterpret_cast<const float4*>(p.bias + colb + 4 * j);
+          v[4 * j] = b4.x; v[4 * j + 1] = b4.y; v[4 * j + 2] = b4.z; v[4 * j + 3] = b4.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < CW; ++j) v[j] = (p.bias && colb + j < p.N) ? p.bias[colb + j] : 0.f;
+      }
+      unsigned int hits = 0;
+#pragma unroll
+      for (int j = 0; j < CW; ++j) {
+        float x = acc_val(r[j]);
+        if (p.col0_bias_only && colb + j == 0) x = 0.f;
+        v[j] += x;
+        if (colb + j < p.N && v[j] >= thr) hits |= 1u << j;
+      }
+      if (hits != 0u) {
+        unsigned int pos = atomicAdd(p.flt.cnt + row, (unsigned int)__popc(hits));
+        unsigned long long* dst = p.flt.cand + (size_t)row * p.flt.cap;
+#pragma unroll
+        for (int j = 0; j < CW; ++j)
+          if (hits & (1u << j)) {
+            if (pos < (unsigned int)p.flt.cap) dst[pos] = compose(f2key(v[j]), (uint32_t)(colb + j));
+            ++pos;
+          }
+      }
+    }
+    return;
+  }
   // fused LayerNorm pieces: (mean, rstd) of the sequence each of this lane's rows belongs to, the rows' running
   // partial sums, and the output row of a last-row-only store (-1: not a last row)
   float2 lnr[NIT];

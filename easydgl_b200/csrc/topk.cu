@@ -12,19 +12,12 @@
 
 namespace edgl {
 
-__device__ __forceinline__ uint32_t f2key(float f) {
-  uint32_t u = __float_as_uint(f);
-  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-__device__ __forceinline__ float key2f(uint32_t k) {
-  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
-}
-__device__ __forceinline__ unsigned long long compose(uint32_t key, uint32_t idx) {
-  return ((unsigned long long)key << 32) | (unsigned long long)(0xffffffffu - idx);
-}
+// f2key / key2f / compose: common.cuh (shared with the candidate-filter epilogue of the logits GEMM)
 
 __global__ void mask_seen_kernel(float* __restrict__ logits, int ld, long long n, int seen_len, long long seen_stride,
-                                 const int64_t* __restrict__ ids, long long col0, long long col1) {
+                                 const int64_t* __restrict__ ids, long long col0, long long col1,
+                                 const int* __restrict__ run_if) {
+  if (run_if && *run_if == 0) return;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const long long b = i / seen_len;
@@ -33,10 +26,10 @@ __global__ void mask_seen_kernel(float* __restrict__ logits, int ld, long long n
 }
 
 int launch_mask_seen(float* logits, int ld, int B, const int64_t* ids, int seen_len, long long seen_stride,
-                     long long col0, long long col1, cudaStream_t st) {
+                     long long col0, long long col1, cudaStream_t st, const int* run_if) {
   const long long n = (long long)B * seen_len;
   if (n == 0) return 0;
-  mask_seen_kernel<<<cdiv(n, 256), 256, 0, st>>>(logits, ld, n, seen_len, seen_stride, ids, col0, col1);
+  mask_seen_kernel<<<cdiv(n, 256), 256, 0, st>>>(logits, ld, n, seen_len, seen_stride, ids, col0, col1, run_if);
   EDGL_LAUNCH_CHECK();
   return 0;
 }
@@ -263,8 +256,9 @@ __device__ void topk_row(const float* __restrict__ p, int ld_vec_ok, int N, int 
 __global__ void __launch_bounds__(256) topk_kernel(const float* __restrict__ logits, int ld, int N, int K, int KP,
                                                    int col_offset, long long out_stride,
                                                    int32_t* __restrict__ idx_out, float* __restrict__ val_out,
-                                                   TopkP2P pp) {
+                                                   TopkP2P pp, const int* __restrict__ run_if) {
   extern __shared__ __align__(16) unsigned long long cand[];  // max(KP, kCandCap) entries
+  if (run_if && *run_if == 0) return;
   const float* p = logits + (long long)blockIdx.x * ld;
   int32_t* io;
   float* vo;
@@ -483,7 +477,7 @@ static int next_pow2(int v) {
 }
 
 int launch_topk(const float* logits, int ld, int B, int N, int K, int col_offset, long long out_stride, int32_t* idx,
-                float* val, cudaStream_t st, const TopkP2P* p2p) {
+                float* val, cudaStream_t st, const TopkP2P* p2p, const int* run_if) {
   if (out_stride == 0) out_stride = K;
   TopkP2P pp;
   memset(&pp, 0, sizeof(pp));
@@ -497,7 +491,7 @@ int launch_topk(const float* logits, int ld, int B, int N, int K, int col_offset
   // instructions per row.
   const char* we = getenv("EDGL_TOPK_WARP");
   const bool use_warp = we != nullptr && we[0] == '1';
-  if (use_warp && K <= 128 && N <= 32 * 96 && B >= 64) {
+  if (use_warp && !run_if && K <= 128 && N <= 32 * 96 && B >= 64) {
     const unsigned grid = (unsigned)((B + 7) / 8);
     if (N <= 32 * 32) topk_warp_kernel<32><<<grid, 256, 0, st>>>(logits, ld, B, N, K, col_offset, out_stride, idx, val, pp);
     else if (N <= 32 * 72) topk_warp_kernel<72><<<grid, 256, 0, st>>>(logits, ld, B, N, K, col_offset, out_stride, idx, val, pp);
@@ -507,7 +501,92 @@ int launch_topk(const float* logits, int ld, int B, int N, int K, int col_offset
   }
   const int KP = next_pow2(K);
   const size_t smem = (size_t)(KP > kCandCap ? KP : kCandCap) * 8;
-  topk_kernel<<<B, 256, smem, st>>>(logits, ld, N, K, KP, col_offset, out_stride, idx, val, pp);
+  topk_kernel<<<B, 256, smem, st>>>(logits, ld, N, K, KP, col_offset, out_stride, idx, val, pp, run_if);
+  EDGL_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---- exact top-K over the candidate list of a row (TopkFilter epilogue of the logits GEMM).  The list holds every
+// column whose logit is >= a lower bound of the row's K-th largest UNMASKED logit, so the top-K of the unmasked
+// candidates is the top-K of the row.  The ids of the row's own sequence (Base.py:156-163) are dropped through a
+// small open-addressing hash in shared memory.  A row whose list overflowed, or that holds fewer than K unmasked
+// candidates (ties / constant rows make the bound useless), raises *redo: the caller's predicated launches then
+// recompute the whole chunk through the materialised logits.
+__global__ void __launch_bounds__(256) topk_select_kernel(const unsigned long long* __restrict__ cand,
+                                                          const unsigned int* __restrict__ cnt, int cap, int K,
+                                                          int col_offset, const int64_t* __restrict__ seen, int seen_len,
+                                                          long long seen_stride, long long col0, long long col1,
+                                                          long long out_stride, int32_t* __restrict__ idx_out,
+                                                          float* __restrict__ val_out, int* __restrict__ redo,
+                                                          int hash_size) {
+  extern __shared__ __align__(16) unsigned long long s[];  // [np <= cap] words, then the hash [hash_size] u32
+  const int tid = threadIdx.x;
+  const long long row = blockIdx.x;
+  const unsigned int n = cnt[row];
+  if (n > (unsigned int)cap || n < (unsigned int)K) {  // block-uniform
+    if (tid == 0) atomicExch(redo, 1);
+    return;
+  }
+  int np = 128;
+  while (np < (int)n) np <<= 1;
+  uint32_t* hash = reinterpret_cast<uint32_t*>(s + cap);
+  for (int i = tid; i < hash_size; i += 256) hash[i] = 0xffffffffu;
+  __syncthreads();
+  if (seen) {
+    for (int l = tid; l < seen_len; l += 256) {
+      const long long id = seen[row * seen_stride + l];
+      if (id >= col0 && id < col1) {
+        const uint32_t v = (uint32_t)(id - col0);
+        uint32_t hpos = (v * 2654435761u) & (uint32_t)(hash_size - 1);
+        while (true) {
+          const uint32_t old = atomicCAS(&hash[hpos], 0xffffffffu, v);
+          if (old == 0xffffffffu || old == v) break;
+          hpos = (hpos + 1) & (uint32_t)(hash_size - 1);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  const unsigned long long* src = cand + row * cap;
+  for (int i = tid; i < np; i += 256) {
+    unsigned long long c = 0ull;  // below every real word (the key of -inf is 0x007fffff)
+    if (i < (int)n) {
+      c = src[i];
+      const uint32_t v = 0xffffffffu - (uint32_t)(c & 0xffffffffull);
+      uint32_t hpos = (v * 2654435761u) & (uint32_t)(hash_size - 1);
+      while (true) {
+        const uint32_t hv = hash[hpos];
+        if (hv == v) { c = 0ull; break; }
+        if (hv == 0xffffffffu) break;
+        hpos = (hpos + 1) & (uint32_t)(hash_size - 1);
+      }
+    }
+    s[i] = c;
+  }
+  bitonic_desc_hybrid(s, np);
+  if (s[K - 1] == 0ull) {  // fewer than K unmasked candidates (block-uniform: read after the sort's last barrier)
+    if (tid == 0) atomicExch(redo, 1);
+    return;
+  }
+  write_topk(s, K, K, col_offset, idx_out + row * out_stride, val_out + row * out_stride);
+}
+
+int launch_topk_select(const unsigned long long* cand, const unsigned int* cnt, int cap, int B, int K, int col_offset,
+                       const int64_t* seen, int seen_len, long long seen_stride, long long col0, long long col1,
+                       long long out_stride, int32_t* idx, float* val, int* redo, cudaStream_t st) {
+  EDGL_REQUIRE(K >= 1 && K <= cap && cap >= 128 && (cap & (cap - 1)) == 0, "topk_select: bad K / cap (%d / %d)", K, cap);
+  if (B == 0) return 0;
+  if (out_stride == 0) out_stride = K;
+  int hs = 256;
+  while (hs < 2 * seen_len) hs <<= 1;
+  const size_t smem = (size_t)cap * 8 + (size_t)hs * 4;
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    EDGL_CUDA(cudaFuncSetAttribute(topk_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  topk_select_kernel<<<B, 256, smem, st>>>(cand, cnt, cap, K, col_offset, seen, seen_len, seen_stride, col0, col1,
+                                           out_stride, idx, val, redo, hs);
   EDGL_LAUNCH_CHECK();
   return 0;
 }

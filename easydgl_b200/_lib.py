@@ -60,6 +60,10 @@ _SIGS = {
     "edgl_topk_merge": (_I, [_P, _P, _I, _I, _I, C.c_int64, C.c_int64, _P, _P, _P]),
     "edgl_time_sinusoid_code": (_I, [_P, _I, _I, _I, _P, _P]),
     "edgl_time_function_code": (_I, [_P, _P, _P, C.c_int64, _I, _P, _P]),
+    "edgl_time_attention": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I,
+                                 _P, _P]),
+    "edgl_row_nonzero": (_I, [_P, C.c_int64, _I, _P, _P]),
+    "edgl_layernorm_last": (_I, [_P, _P, _P, C.c_int64, _I, C.c_float, _P, _P]),
     "edgl_embedding_lookup": (_I, [_P, _I, _I, _I, _I, _P, C.c_int64, _P, _P]),
     "edgl_embed": (_I, [_P, _P, _P, _I, _P, _P, _P, _P]),
     "edgl_attention_layer": (_I, [_P, _I, _P, _I, _P, _I, _P, _P, _P, _I, _I, _P, _P, _P]),

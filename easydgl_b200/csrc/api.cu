@@ -1321,6 +1321,31 @@ int edgl_layernorm(const float* x, const float* gamma, const float* beta, int B,
   return launch_layernorm(x, gamma, beta, B, L, C, out, false, (cudaStream_t)stream);
 }
 
+int edgl_time_attention(const float* Q, const float* K, const float* V, const uint8_t* key_mask,
+                        const uint8_t* query_mask, const float* pos_k, const float* pos_v, int time_mode,
+                        const void* intervals, const float* time_k, const float* time_v, int vocab,
+                        const float* basis_freq, const float* phase, const float* U, float* TC, const float* residual,
+                        int B, int Tq, int Tk, int C, int num_heads, int causality, float* out, void* stream) {
+  if (!Q || !K || !V || !out) return set_error(EDGL_EINVAL, "null argument");
+  EDGL_REQUIRE(B >= 0 && Tq >= 0 && Tk >= 1 && C >= 1, "time_attention: bad shape");
+  return launch_time_attention(Q, K, V, key_mask, query_mask, pos_k, pos_v, time_mode, intervals, time_k, time_v, vocab,
+                               basis_freq, phase, U, TC, residual, B, Tq, Tk, C, num_heads, causality, out,
+                               (cudaStream_t)stream);
+}
+
+int edgl_row_nonzero(const float* x, int64_t rows, int C, uint8_t* out, void* stream) {
+  if (!x || !out) return set_error(EDGL_EINVAL, "null argument");
+  EDGL_REQUIRE(rows >= 0 && C >= 1, "row_nonzero: bad shape");
+  return launch_row_nonzero(x, rows, C, out, (cudaStream_t)stream);
+}
+
+int edgl_layernorm_last(const float* x, const float* gamma, const float* beta, int64_t rows, int C, float eps, float* out,
+                        void* stream) {
+  if (!x || !gamma || !beta || !out) return set_error(EDGL_EINVAL, "null argument");
+  EDGL_REQUIRE(rows >= 0 && C >= 1 && eps >= 0.f, "layernorm_last: bad shape");
+  return launch_rownorm(x, gamma, beta, rows, C, eps, out, (cudaStream_t)stream);
+}
+
 int edgl_dense(const float* x, const float* w, const float* b, int M, int K, int N, int act, float* out,
                void* stream) {
   if (!x || !w || !out) return set_error(EDGL_EINVAL, "null argument");

@@ -223,6 +223,15 @@ int launch_tpp_terms(const float* lam, const int64_t* positions, const int64_t* 
 int launch_reduce(const float* x, long long n, int squares, double scale, double* out, int accumulate, cudaStream_t st);
 int launch_loss_combine(const double* acc, int num_blocks, double ct_scale, float* loss_out, cudaStream_t st);
 
+// time_attn.cu: attention cores of the Ti / Tf / Tg baseline layers (temporal.py:15-264) and their helpers
+int launch_time_attention(const float* Q, const float* K, const float* V, const uint8_t* kmask, const uint8_t* qmask,
+                          const float* pos_k, const float* pos_v, int mode, const void* intervals, const float* tk,
+                          const float* tv, int vocab, const float* freq, const float* phase, const float* U, float* TC,
+                          const float* R, int B, int Tq, int Tk, int C, int h, int causal, float* out, cudaStream_t st);
+int launch_row_nonzero(const float* x, long long rows, int C, uint8_t* out, cudaStream_t st);
+int launch_rownorm(const float* x, const float* gamma, const float* beta, long long rows, int C, float eps, float* out,
+                   cudaStream_t st);
+
 int launch_mask_seen(float* logits, int ld, int B, const int64_t* ids, int seen_len, long long seen_stride,
                      long long col0, long long col1, cudaStream_t st, const int* run_if = nullptr);
 // Fused candidate exchange over peer memory (multi-GPU): when `dest` is set the top-K kernel writes row R's

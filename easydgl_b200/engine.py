@@ -365,6 +365,65 @@ def time_function_code(x: torch.Tensor, basis_freq: torch.Tensor, phase: torch.T
     return out
 
 
+def row_nonzero(x: torch.Tensor) -> torch.Tensor:
+    """tf.sign(tf.reduce_sum(tf.abs(x), -1)) as uint8 (key / query masks, temporal.py:65, 87)."""
+    lib = _lib.load()
+    x = _req(x, torch.float32, "x")
+    out = torch.empty(tuple(x.shape[:-1]), dtype=torch.uint8, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib.edgl_row_nonzero(x.data_ptr(), x.numel() // x.shape[-1], int(x.shape[-1]), out.data_ptr(), _stream()))
+    return out
+
+
+def layernorm_last(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-8) -> torch.Tensor:
+    """module.normalize.layernorm (normalize.py:9-19): last-axis moments."""
+    lib = _lib.load()
+    x = _req(x, torch.float32, "x")
+    gamma = _req(gamma, torch.float32, "gamma", x.device)
+    beta = _req(beta, torch.float32, "beta", x.device)
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        check(lib.edgl_layernorm_last(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), x.numel() // x.shape[-1],
+                                      int(x.shape[-1]), float(eps), out.data_ptr(), _stream()))
+    return out
+
+
+def time_attention(Q, K, V, num_heads, key_mask=None, query_mask=None, pos_k=None, pos_v=None, time_mode=0,
+                   intervals=None, time_k=None, time_v=None, basis_freq=None, phase=None, U=None, residual=None,
+                   causality=False):
+    """Attention core of the Ti / Tf / Tg layers (edgl_time_attention).  Returns out [B,Tq,C] (and TC for mode 3)."""
+    lib = _lib.load()
+    Q = _req(Q, torch.float32, "Q")
+    dev = Q.device
+    K = _req(K, torch.float32, "K", dev)
+    V = _req(V, torch.float32, "V", dev)
+    B, Tq, C = Q.shape
+    Tk = int(K.shape[1])
+
+    def opt(t, dtype, name):
+        return None if t is None else _req(t, dtype, name, dev)
+    key_mask = opt(key_mask, torch.uint8, "key_mask")
+    query_mask = opt(query_mask, torch.uint8, "query_mask")
+    pos_k, pos_v = opt(pos_k, torch.float32, "pos_k"), opt(pos_v, torch.float32, "pos_v")
+    time_k, time_v = opt(time_k, torch.float32, "time_k"), opt(time_v, torch.float32, "time_v")
+    basis_freq, phase = opt(basis_freq, torch.float32, "basis_freq"), opt(phase, torch.float32, "phase")
+    U, residual = opt(U, torch.float32, "U"), opt(residual, torch.float32, "residual")
+    if time_mode != 0:
+        intervals = _req(intervals, torch.int64 if time_mode == 1 else torch.float32, "intervals", dev)
+        if tuple(intervals.shape) != (B, Tq, Tk):
+            raise ValueError("intervals must be [B,Tq,Tk]")
+    out = torch.empty_like(Q)
+    TC = torch.empty((B, Tq, num_heads, C), dtype=torch.float32, device=dev) if time_mode == 3 else None
+    vocab = int(time_k.shape[0]) if time_k is not None else 0
+    with torch.cuda.device(dev):
+        check(lib.edgl_time_attention(Q.data_ptr(), K.data_ptr(), V.data_ptr(), _ptr(key_mask), _ptr(query_mask),
+                                      _ptr(pos_k), _ptr(pos_v), int(time_mode), _ptr(intervals), _ptr(time_k),
+                                      _ptr(time_v), vocab, _ptr(basis_freq), _ptr(phase), _ptr(U), _ptr(TC),
+                                      _ptr(residual), B, Tq, Tk, C, int(num_heads), int(bool(causality)),
+                                      out.data_ptr(), _stream()))
+    return (out, TC) if time_mode == 3 else out
+
+
 def embedding_lookup(table: torch.Tensor, ids: torch.Tensor, zero_pad: bool, scale: bool) -> torch.Tensor:
     lib = _lib.load()
     table = _req(table, torch.float32, "table")

@@ -51,6 +51,17 @@ class PositionCoding(object):
         return self.pembs(pos)
 
 
+class TimeIntervalCoding(object):
+    """coding.py:82-94 (Li et al., TiSASRec): a learned embedding per clipped integer time interval."""
+
+    def __init__(self, vocab_size, num_units, l2_reg=0., scope="coding/tim", device="cuda:0", initializer=None):
+        self.pembs = Embedding(vocab_size, num_units, l2_reg, zero_pad=False, scale=False, initializer=initializer,
+                               device=device)
+
+    def code(self, inputs):
+        return self.pembs(inputs)
+
+
 class TimeFunctionCoding(object):
     """coding.py:97-122 (Xu et al., TGAT): learnable harmonic (Bochner / Mercer) time kernel
     ``cos(t * basis_freq + phase)``; ``basis_freq`` initialised to linspace(0, 9, d), ``phase`` to zeros."""

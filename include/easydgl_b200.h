@@ -196,6 +196,29 @@ int edgl_time_sinusoid_code(const float* ts, int B, int L, int d, float* out, vo
  * rank 4): x fp32 [n] (any leading shape, flattened) -> out [n,d] = cos(x * basis_freq + phase). */
 int edgl_time_function_code(const float* x, const float* basis_freq, const float* phase, int64_t n, int d, float* out,
                             void* stream);
+/* Attention core of T.TiMultiHeadAttention (temporal.py:15-109; time_mode 1), T.TfMultiHeadAttention
+ * (temporal.py:112-185; time_mode 2) and T.TgMultiHeadAttention (temporal.py:188-264; time_mode 3) after their dense
+ * projections; time_mode 0 is plain multi-head attention.  Q [B,Tq,C], K / V [B,Tk,C] fp32; key_mask [B,Tk] /
+ * query_mask [B,Tq] uint8 or null (temporal.py:65-70, 87-90); pos_k / pos_v [Tk,C] position codes added to K / V or null
+ * (temporal.py:49-50, 57, 98); causality != 0 = future blinding (temporal.py:73-79).
+ *   mode 1: intervals int64 [B,Tq,Tk] (clipped to [0, vocab)), time_k / time_v [vocab,C] interval embeddings
+ *           (time_v may be null): s += Q . time_k[iv], o += P time_v[iv]            (temporal.py:51-52, 58, 99)
+ *   mode 2: intervals fp32 [B,Tq,Tk]: s += Q . cos(iv basis_freq + phase) (head slice)  (temporal.py:141, 146)
+ *   mode 3: intervals fp32, U [B,Tq,h,C] = the time half of the key projection applied to the query (W_k2[:, head]
+ *           Q[head]): s += U . cos(iv basis_freq + phase); TC [B,Tq,h,C] (output) = sum_k P cos(.), the time half of
+ *           the value product before W_v2                                         (temporal.py:212-220, 249-251)
+ * out [B,Tq,C] = softmax-weighted values + residual (null = none).  Exact fp32. */
+int edgl_time_attention(const float* Q, const float* K, const float* V, const uint8_t* key_mask,
+                        const uint8_t* query_mask, const float* pos_k, const float* pos_v, int time_mode,
+                        const void* intervals, const float* time_k, const float* time_v, int vocab,
+                        const float* basis_freq, const float* phase, const float* U, float* TC, const float* residual,
+                        int B, int Tq, int Tk, int C, int num_heads, int causality, float* out, void* stream);
+/* tf.sign(tf.reduce_sum(tf.abs(x), -1)) of the key / query masking (temporal.py:65, 87): x [rows,C] -> out [rows] 0/1. */
+int edgl_row_nonzero(const float* x, int64_t rows, int C, uint8_t* out, void* stream);
+/* module.normalize.layernorm (normalize.py:9-19): moments over the last axis,
+ * gamma (x - mean) / sqrt(var + eps) + beta; x [rows,C]. */
+int edgl_layernorm_last(const float* x, const float* gamma, const float* beta, int64_t rows, int C, float eps, float* out,
+                        void* stream);
 /* C.Embedding(vocab,d,zero_pad,scale)(ids)  (coding.py:45-64): table [vocab,d] raw variable. */
 int edgl_embedding_lookup(const float* table, int vocab, int d, int zero_pad, int scale, const int64_t* ids,
                           int64_t n_ids, float* out, void* stream);

@@ -247,6 +247,95 @@ def mau(queries, keys, kmask, intervals, marks, w, num_units, num_heads, num_eve
 # ----------------------------------------------------------------------------
 # src/model/EasyDGL.py
 # ----------------------------------------------------------------------------
+def _time_attn_softmax(scores, keys, causality, num_heads, masks=None):
+    """Scale is applied by the caller.  Key masking from ``keys`` (temporal.py:64-70,149-155) or from a given
+    ``masks`` [N,T_q,T_k] (temporal.py:232-233), causality (temporal.py:72-79), softmax (temporal.py:82)."""
+    hN, Tq, Tk = scores.shape
+    if masks is None:
+        km = torch.sign(keys.abs().sum(-1))                                   # [N,T_k]
+        km = km.repeat(num_heads, 1).unsqueeze(1).expand(hN, Tq, Tk)
+    else:
+        km = masks.repeat(num_heads, 1, 1) if masks.shape[0] * num_heads == hN else masks
+    fill = torch.full_like(scores, MASK_FILL)
+    scores = torch.where(km == 0, fill, scores)
+    if causality:
+        tril = torch.tril(torch.ones(Tq, Tk, dtype=scores.dtype)).unsqueeze(0).expand(hN, Tq, Tk)
+        scores = torch.where(tril == 0, fill, scores)
+    return torch.softmax(scores, dim=-1)
+
+
+def ti_attention(queries, keys, intervals, w, pos_k, pos_v, tab_k, tab_v, num_heads, causality=True):
+    """TiMultiHeadAttention.__call__ (temporal.py:37-109), eval mode, literal: the [h*N,T_q,T_k,C/h] interval-code
+    tensors are materialised like the reference.  pos_* [T,C] = PositionCoding tables (rows 0..T-1, coding.py:76-79),
+    tab_* [vocab,C] = TimeIntervalCoding tables (coding.py:93-94), intervals int64 [N,T_q,T_k]."""
+    h = num_heads
+    N, T, _ = queries.shape
+    Q = queries @ w["q_w"] + w["q_b"]
+    K = keys @ w["k_w"] + w["k_b"]
+    V = keys @ w["v_w"] + w["v_b"]
+    Q_, K_, V_ = fold_heads(Q, h), fold_heads(K, h), fold_heads(V, h)
+    Kp = fold_heads(pos_k[:T].unsqueeze(0).expand(N, T, -1), h)
+    Vp = fold_heads(pos_v[:T].unsqueeze(0).expand(N, T, -1), h)
+    Kt = torch.cat(torch.split(tab_k[intervals], tab_k.shape[1] // h, dim=3), dim=0)   # [hN,T_q,T_k,dh]
+    Vt = torch.cat(torch.split(tab_v[intervals], tab_v.shape[1] // h, dim=3), dim=0)
+    out = Q_ @ K_.transpose(1, 2) + Q_ @ Kp.transpose(1, 2) + (Kt @ Q_.unsqueeze(3)).squeeze(3)   # temporal.py:55-59
+    out = out / (K_.shape[-1] ** 0.5)
+    P = _time_attn_softmax(out, keys, causality, h)
+    qm = torch.sign(queries.abs().sum(-1)).repeat(h, 1).unsqueeze(-1)                 # temporal.py:87-90
+    P = P * qm
+    o = P @ V_ + P @ Vp + (P.unsqueeze(2) @ Vt).squeeze(2)                            # temporal.py:96-100
+    return unfold_heads(o, h) + queries                                                # temporal.py:103-106
+
+
+def tf_attention(queries, keys, intervals, w, pos_k, basis_freq, phase, num_heads, causality=True):
+    """TfMultiHeadAttention.__call__ (temporal.py:126-185), eval mode, literal.  intervals fp32 [N,T_q,T_k]."""
+    h = num_heads
+    N, T, _ = queries.shape
+    dtype = queries.dtype
+    Q = queries @ w["q_w"] + w["q_b"]
+    K = keys @ w["k_w"] + w["k_b"]
+    V = keys @ w["v_w"] + w["v_b"]
+    Q_, K_, V_ = fold_heads(Q, h), fold_heads(K, h), fold_heads(V, h)
+    Kp = fold_heads(pos_k[:T].unsqueeze(0).expand(N, T, -1), h)
+    code = time_function_code(intervals, basis_freq, phase, dtype)                     # [N,T_q,T_k,C]
+    Kt = torch.cat(torch.split(code, code.shape[3] // h, dim=3), dim=0)
+    out = Q_ @ K_.transpose(1, 2) + Q_ @ Kp.transpose(1, 2) + (Kt @ Q_.unsqueeze(3)).squeeze(3)   # temporal.py:144-147
+    out = out / (K_.shape[-1] ** 0.5)
+    P = _time_attn_softmax(out, keys, causality, h)
+    return unfold_heads(P @ V_, h) + queries                                           # temporal.py:176-183
+
+
+def layernorm_last(x, gamma, beta, eps=1e-8):
+    """module.normalize.layernorm (normalize.py:9-19)."""
+    mean = x.mean(-1, keepdim=True)
+    var = ((x - mean) ** 2).mean(-1, keepdim=True)
+    return gamma * ((x - mean) / torch.sqrt(var + eps)) + beta
+
+
+def tg_attention(queries, keys, masks, intervals, w, basis_freq, phase, num_heads, causality=True):
+    """TgMultiHeadAttention.__call__ (temporal.py:204-264), eval mode, literal: [N,T_q,T_k,2C] keys are built and
+    projected like the reference.  masks [N,T_q,T_k] (or [h*N,...]); output [N,T_q,2C]."""
+    h = num_heads
+    N, Tq, C = queries.shape
+    dtype = queries.dtype
+    q_t = time_function_code(torch.zeros(N, Tq, 1), basis_freq, phase, dtype)          # [N,T_q,1,C]
+    q4 = torch.cat([queries.unsqueeze(2), q_t], dim=-1)                                # [N,T_q,1,2C]
+    k_t = time_function_code(intervals, basis_freq, phase, dtype)                      # [N,T_q,T_k,C]
+    k4 = torch.cat([keys.unsqueeze(1).expand(N, Tq, keys.shape[1], keys.shape[2]), k_t], dim=-1)
+    Q = q4 @ w["q_w"] + w["q_b"]
+    K = k4 @ w["k_w"] + w["k_b"]
+    V = k4 @ w["v_w"] + w["v_b"]
+    split = lambda x: torch.cat(torch.split(x, x.shape[3] // h, dim=3), dim=0)         # noqa: E731
+    Q_, K_, V_ = split(Q), split(K), split(V)
+    out = (Q_ @ K_.transpose(2, 3)).squeeze(2)                                         # [hN,T_q,T_k]
+    out = out / (K_.shape[-1] ** 0.5)
+    P = _time_attn_softmax(out, None, causality, h, masks=masks)
+    o = (P.unsqueeze(2) @ V_).squeeze(2)                                               # [hN,T_q,dh]
+    o = unfold_heads(o, h)
+    o = o @ w["o_w"] + w["o_b"] + q4.squeeze(2)                                        # temporal.py:260-261
+    return layernorm_last(o, w["ln_g"], w["ln_b"])
+
+
 def gelu(x: torch.Tensor) -> torch.Tensor:
     """EasyDGL.gelu (EasyDGL.py:19-32): exact erf form (Q18)."""
     cdf = 0.5 * (1.0 + torch.erf(x / math.sqrt(2.0)))

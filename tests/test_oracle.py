@@ -321,3 +321,42 @@ def test_train_forward_loss_restatement():
     bl = O.biased_likelihood(lam.clone(), nm, iv)
     want = -(torch.log(lam[0, 0, 1]) - lam[0, 0].sum() * iv[0, 0] * .5) / 1.0
     assert abs(float(bl) - float(want)) < 1e-12
+
+
+def test_tg_attention_decomposition_matches_literal():
+    """TgMultiHeadAttention (temporal.py:204-264): the facade never builds the [N,T_q,T_k,2C] keys - it splits the K / V
+    kernels into a per-key half and a time half (moved to the query side for the scores, applied after the weighted sum
+    of the time codes for the values).  That algebra, restated in fp64 torch, must equal the literal restatement."""
+    import numpy as np
+    g = torch.Generator().manual_seed(4)
+    N, T, C, h = 2, 9, 8, 2
+    dh = C // h
+    x = torch.randn(N, T, C, generator=g, dtype=torch.float64)
+    ts = torch.cumsum(torch.rand(N, T, generator=g), 1)
+    iv = (ts.unsqueeze(2) - ts.unsqueeze(1)).clamp_min(0.0).float()
+    masks = torch.ones(N, T, T, dtype=torch.float64)
+    masks[1, :, :3] = 0
+    freq = torch.from_numpy(np.linspace(0, 9, C).astype(np.float32))
+    phase = torch.randn(C, generator=g)
+    w = {"q_w": torch.randn(2 * C, C, generator=g, dtype=torch.float64), "q_b": torch.randn(C, generator=g, dtype=torch.float64),
+         "k_w": torch.randn(2 * C, C, generator=g, dtype=torch.float64), "k_b": torch.randn(C, generator=g, dtype=torch.float64),
+         "v_w": torch.randn(2 * C, C, generator=g, dtype=torch.float64), "v_b": torch.randn(C, generator=g, dtype=torch.float64),
+         "o_w": torch.randn(C, 2 * C, generator=g, dtype=torch.float64), "o_b": torch.randn(2 * C, generator=g, dtype=torch.float64),
+         "ln_g": torch.ones(2 * C, dtype=torch.float64), "ln_b": torch.zeros(2 * C, dtype=torch.float64)}
+    ref = O.tg_attention(x, x, masks, iv, w, freq, phase, h, True)
+    code = O.time_function_code(iv, freq, phase, torch.float64)                    # [N,T,T,C]
+    q2 = torch.cat([x, O.time_function_code(torch.zeros(N, T, 1), freq, phase, torch.float64).squeeze(2)], -1)
+    Q = q2 @ w["q_w"] + w["q_b"]
+    A_k, A_v = x @ w["k_w"][:C] + w["k_b"], x @ w["v_w"][:C] + w["v_b"]
+    out = torch.zeros(N, T, C, dtype=torch.float64)
+    for hd in range(h):
+        sl = slice(hd * dh, (hd + 1) * dh)
+        U = Q[:, :, sl] @ w["k_w"][C:, sl].t()                                      # [N,T,C]
+        s = (Q[:, :, sl] @ A_k[:, :, sl].transpose(1, 2) + torch.einsum("nqc,nqkc->nqk", U, code)) / dh ** 0.5
+        s = torch.where(masks == 0, torch.full_like(s, O.MASK_FILL), s)
+        s = torch.where(torch.tril(torch.ones(T, T)) == 0, torch.full_like(s, O.MASK_FILL), s)
+        P = torch.softmax(s, -1)
+        TC = torch.einsum("nqk,nqkc->nqc", P, code)
+        out[:, :, sl] = P @ A_v[:, :, sl] + TC @ w["v_w"][C:, sl]
+    got = O.layernorm_last(out @ w["o_w"] + w["o_b"] + q2, w["ln_g"], w["ln_b"])
+    assert float((got - ref).abs().max()) < 1e-10

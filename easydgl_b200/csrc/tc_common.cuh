@@ -109,6 +109,35 @@ __device__ __forceinline__ float gelu_fit(float x) {
   return fmaf(fabsf(x), fmaf(e, -0.5f, 0.5f), 0.5f * x);
 }
 
+// the same fit on two values at once with packed fp32x2 arithmetic (sm_100 FFMA2 / FMUL2: one issue slot for two IEEE
+// operations, bit-identical to the scalar form): 9 instead of 14 issue slots per element
+__device__ __forceinline__ void gelu_fit2(float& x0, float& x1) {
+  typedef unsigned long long f2;
+  auto pk = [](float a, float b) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; };
+  auto fma2 = [](f2 a, f2 b, f2 c) { f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; };
+  auto mul2 = [](f2 a, f2 b) { f2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; };
+  const float a0 = fabsf(x0), a1 = fabsf(x1);
+  const float t0 = fminf(a0 * 0.70710678118654752440f, 4.0f), t1 = fminf(a1 * 0.70710678118654752440f, 4.0f);
+  const f2 t = pk(t0, t1);
+  f2 p = pk(4.5358559873420745e-05f, 4.5358559873420745e-05f);
+  p = fma2(p, t, pk(-0.00044550723396241665f, -0.00044550723396241665f));
+  p = fma2(p, t, pk(0.0014894399791955948f, 0.0014894399791955948f));
+  p = fma2(p, t, pk(0.0007746326737105846f, 0.0007746326737105846f));
+  p = fma2(p, t, pk(-0.02825368382036686f, -0.02825368382036686f));
+  p = fma2(p, t, pk(0.14848162233829498f, 0.14848162233829498f));
+  p = fma2(p, t, pk(0.9184163808822632f, 0.9184163808822632f));
+  p = fma2(p, t, pk(1.6279085874557495f, 1.6279085874557495f));
+  float q0, q1;
+  const f2 tp = mul2(pk(-t0, -t1), p);
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(q0), "=f"(q1) : "l"(tp));
+  float e0, e1;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(q0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(q1));
+  const f2 w = fma2(pk(e0, e1), pk(-0.5f, -0.5f), pk(0.5f, 0.5f));
+  const f2 r = fma2(pk(a0, a1), w, mul2(pk(0.5f, 0.5f), pk(x0, x1)));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(r));
+}
+
 __device__ __forceinline__ float gelu_erf_exact(float x) {
   return x * (0.5f * (1.0f + erff(x * 0.70710678118654752440f)));  // EasyDGL.py:31-32
 }
@@ -240,7 +269,10 @@ __device__ __forceinline__ void epilogue_tile(const P& p, uint32_t tmem_acc, int
             float2 v = make_float2(acc_val(r8[4 * j + 2 * h8]), acc_val(r8[4 * j + 2 * h8 + 1]));
             if (p.col0_bias_only && col == 0) v.x = 0.f;
             v.x += add[h8][j].x; v.y += add[h8][j].y;
-            if (ACT == ACT_GELU) { v.x = (p.gelu_fit ? gelu_fit(v.x) : gelu_erf_exact(v.x)); v.y = (p.gelu_fit ? gelu_fit(v.y) : gelu_erf_exact(v.y)); }
+            if (ACT == ACT_GELU) {
+              if (p.gelu_fit) gelu_fit2(v.x, v.y);
+              else { v.x = gelu_erf_exact(v.x); v.y = gelu_erf_exact(v.y); }
+            }
             if (ACT == ACT_RELU) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); }
             v.x += res[h8][j].x; v.y += res[h8][j].y;
             if (row < p.M) {
@@ -296,7 +328,10 @@ __device__ __forceinline__ void epilogue_tile(const P& p, uint32_t tmem_acc, int
         if (p.col0_bias_only && col == 0) v.x = 0.f;
         if (p.pbias) { v.x += pp[itr].x; v.y += pp[itr].y; v.z += pp[itr].z; v.w += pp[itr].w; }
         v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
-        if (ACT == ACT_GELU) { v.x = (p.gelu_fit ? gelu_fit(v.x) : gelu_erf_exact(v.x)); v.y = (p.gelu_fit ? gelu_fit(v.y) : gelu_erf_exact(v.y)); v.z = (p.gelu_fit ? gelu_fit(v.z) : gelu_erf_exact(v.z)); v.w = (p.gelu_fit ? gelu_fit(v.w) : gelu_erf_exact(v.w)); }
+        if (ACT == ACT_GELU) {
+          if (p.gelu_fit) { gelu_fit2(v.x, v.y); gelu_fit2(v.z, v.w); }
+          else { v.x = gelu_erf_exact(v.x); v.y = gelu_erf_exact(v.y); v.z = gelu_erf_exact(v.z); v.w = gelu_erf_exact(v.w); }
+        }
         if (ACT == ACT_RELU) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
         if (p.R) { v.x += rr[itr].x; v.y += rr[itr].y; v.z += rr[itr].z; v.w += rr[itr].w; }
         if (row < p.M) {

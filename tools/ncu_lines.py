@@ -1,9 +1,11 @@
 #!/usr/bin/env python
 """Per-CUDA-source-line share of executed warp instructions and stall samples of an `ncu --set full --import-source on`
-report (needs -lineinfo):  python tools/ncu_lines.py rep.ncu-rep [min_pct]"""
+report (needs -lineinfo):  python tools/ncu_lines.py rep.ncu-rep [min_pct] [kernel-name-regex]"""
 import csv, subprocess, sys
 rep = sys.argv[1]; thr = float(sys.argv[2]) if len(sys.argv) > 2 else 0.5
-out = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '--print-source', 'cuda,sass'], capture_output=True, text=True).stdout
+cmd = ['ncu', '-i', rep, '--page', 'source', '--csv', '--print-source', 'cuda,sass']
+if len(sys.argv) > 3: cmd += ['--kernel-name', 'regex:' + sys.argv[3]]
+out = subprocess.run(cmd, capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hdr = None; lines = {}; order = []
 for r in rows:

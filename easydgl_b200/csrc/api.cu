@@ -48,6 +48,28 @@ const char* const kStageNames[ST_COUNT] = {"embed", "ln_in", "qkvt_gemm", "atten
                                            "ff1_gemm", "ff2_gemm", "ln_ff", "tr_gemm", "ln_out", "logits_gemm",
                                            "mask_seen", "topk", "end"};
 
+int g_edgl_stage = -1;
+int ablation_gemm_bits() {
+  const char* e = getenv("EDGL_ABL_GEMM");
+  if (!e) return 0;
+  int idx = -1;
+  switch (g_edgl_stage) {
+    case ST_QKVT_GEMM: idx = 0; break;
+    case ST_AO_GEMM: idx = 1; break;
+    case ST_FF1_GEMM: idx = 2; break;
+    case ST_FF2_GEMM: idx = 3; break;
+    case ST_TR_GEMM: idx = 4; break;
+    case ST_LOGITS_GEMM: idx = 5; break;
+    default: return 0;
+  }
+  if ((int)strlen(e) <= idx || e[idx] < '0' || e[idx] > '3') return 0;
+  return e[idx] - '0';
+}
+int ablation_attn_mask() {
+  const char* e = getenv("EDGL_ABL_ATTN");
+  return e ? atoi(e) : 0;
+}
+
 }  // namespace edgl
 
 using namespace edgl;
@@ -123,6 +145,7 @@ namespace {
 
 // record an event BEFORE the stage's kernel is enqueued; the time to the next mark belongs to `stage`
 inline void mark(edgl_handle* h, int stage, cudaStream_t st) {
+  g_edgl_stage = stage;
   if (!h->prof_on || h->prof_n >= h->prof_ev.size()) return;
   cudaEventRecord(h->prof_ev[h->prof_n], st);
   h->prof_stage[h->prof_n] = stage;

@@ -22,7 +22,8 @@ using namespace f16c;
 
 // NT = number of 8-key tiles held in registers (L <= 8*NT); HPC heads are processed by one CTA in turn.
 // MAXREG bounds the registers per thread and so the CTAs per SM (7 warps/CTA at L = 100: 128 -> 2, 80 -> 3, 72 -> 4).
-template <int DH, int NT, int MAXREG>
+// ABL: precision ablation (common.cuh; tools/ablation.py) - individual lo products left out.  0 on the product path.
+template <int DH, int NT, int MAXREG, int ABL = 0>
 __global__ void __maxnreg__(MAXREG) attention_f16_kernel(AttnArgs a, int hpc) {
   using LY = F16Layout<DH>;
   constexpr int E = LY::E, KD = LY::KD, ND = LY::ND, NC = LY::NC, MT = LY::MT, SKW = LY::SKW, RB = LY::RB;
@@ -216,10 +217,10 @@ __global__ void __maxnreg__(MAXREG) attention_f16_kernel(AttnArgs a, int hpc) {
             if (n0 + j < NT) ldsm_x4(kb[j], ks_addr + (n0 + j) * 8 * RB + ks * 32);
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            if (n0 + j < NT) mma_f16(P[n0 + j], ql[ks], kb[j][0], kb[j][1]);
+            if ((ABL & 1) == 0 && n0 + j < NT) mma_f16(P[n0 + j], ql[ks], kb[j][0], kb[j][1]);
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            if (n0 + j < NT) mma_f16(P[n0 + j], qh[ks], kb[j][2], kb[j][3]);
+            if ((ABL & 2) == 0 && n0 + j < NT) mma_f16(P[n0 + j], qh[ks], kb[j][2], kb[j][3]);
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             if (n0 + j < NT) mma_f16(P[n0 + j], qh[ks], kb[j][0], kb[j][1]);
@@ -280,7 +281,7 @@ __global__ void __maxnreg__(MAXREG) attention_f16_kernel(AttnArgs a, int hpc) {
       }
       // ---- H = P T : accumulator = H * 2^14 * scale(T); |H * scale(T)| < 2^15 because rows of P sum to 1
       float H[ND][4];
-      pv_product16<DH, NT>(P, ts_addr, H);
+      pv_product16<DH, NT, ABL>(P, ts_addr, H);
       // ---- intensity MLP: Z = sigmoid([H, span] W1 + b1); dot with w per event (temporal.py:287-305)
       uint32_t hh_[KD][4], hl_[KD][4];
 #pragma unroll
@@ -321,9 +322,11 @@ __global__ void __maxnreg__(MAXREG) attention_f16_kernel(AttnArgs a, int hpc) {
             for (int j = 0; j < 4; ++j)
               wb[j] = *reinterpret_cast<const uint4*>(w1g + (tq * 4 + j) * 8 * SKW + ks * 16);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) mma_f16(z[j], hl_[ks], wb[j].x, wb[j].y);
+            for (int j = 0; j < 4; ++j)
+              if ((ABL & 16) == 0) mma_f16(z[j], hl_[ks], wb[j].x, wb[j].y);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) mma_f16(z[j], hh_[ks], wb[j].z, wb[j].w);
+            for (int j = 0; j < 4; ++j)
+              if ((ABL & 32) == 0) mma_f16(z[j], hh_[ks], wb[j].z, wb[j].w);
 #pragma unroll
             for (int j = 0; j < 4; ++j) mma_f16(z[j], hh_[ks], wb[j].x, wb[j].y);
           }
@@ -421,7 +424,7 @@ __global__ void __maxnreg__(MAXREG) attention_f16_kernel(AttnArgs a, int hpc) {
           if (n0 + j < NT) mk[j] = *reinterpret_cast<const uint2*>(Ms + ((n0 + j) * 8 + g) * 8 + 2 * t);
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          if (n0 + j < NT) mma_f16(G[j], ll, mk[j].x, mk[j].y);
+          if ((ABL & 64) == 0 && n0 + j < NT) mma_f16(G[j], ll, mk[j].x, mk[j].y);
 #pragma unroll
         for (int j = 0; j < 4; ++j)
           if (n0 + j < NT) mma_f16(G[j], lh, mk[j].x, mk[j].y);
@@ -454,7 +457,7 @@ __global__ void __maxnreg__(MAXREG) attention_f16_kernel(AttnArgs a, int hpc) {
       }
       // ---- O = (G o P) V : accumulator = O * 2^14 * scale(lam row) * scale(G o P row) * scale(V)
       float O[ND][4];
-      pv_product16<DH, NT>(P, vs_addr, O);
+      pv_product16<DH, NT, ABL>(P, vs_addr, O);
       constexpr float k2m14 = 1.0f / 16384.f;
       const float fa = isv * isga, fb = isv * isgb;
       const float fa2 = k2m14 * isla, fb2 = k2m14 * islb;
@@ -481,12 +484,12 @@ __global__ void __maxnreg__(MAXREG) attention_f16_kernel(AttnArgs a, int hpc) {
   }
 }
 
-template <int DH, int NT, int MAXREG>
+template <int DH, int NT, int MAXREG, int ABL = 0>
 int launch_f16_t(const AttnArgs& a, int hpc, cudaStream_t st) {
   using LY = F16Layout<DH>;
   const size_t smem = LY::smem_bytes(NT);
   if (smem > 227 * 1024) return 1;
-  auto kern = attention_f16_kernel<DH, NT, MAXREG>;
+  auto kern = attention_f16_kernel<DH, NT, MAXREG, ABL>;
   EDGL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // several ~50 KB CTAs per SM: ask for the largest shared-memory carve-out, or the driver's default split caps residency
   EDGL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -538,6 +541,18 @@ int launch_attention_f16(const AttnArgs& a, cudaStream_t st) {
   if (a.L <= 32) return launch_f16_t<16, 4, 128>(a, hpc, st);
   if (a.L <= 104) {
     // 72 registers -> 4 CTAs of 7 warps per SM: measured best at C2 (1.34 ms; 80 -> 1.42, 128 -> 1.44)
+    if (const int abl = ablation_attn_mask()) {  // precision ablation (tools/ablation.py): the instantiated masks only
+      switch (abl) {
+        case 3: return launch_f16_t<16, 13, 72, 3>(a, hpc, st);
+        case 4: return launch_f16_t<16, 13, 72, 4>(a, hpc, st);
+        case 8: return launch_f16_t<16, 13, 72, 8>(a, hpc, st);
+        case 12: return launch_f16_t<16, 13, 72, 12>(a, hpc, st);
+        case 48: return launch_f16_t<16, 13, 72, 48>(a, hpc, st);
+        case 64: return launch_f16_t<16, 13, 72, 64>(a, hpc, st);
+        case 127: return launch_f16_t<16, 13, 72, 127>(a, hpc, st);
+        default: return set_error(-1, "EDGL_ABL_ATTN=%d is not instantiated (3, 4, 8, 12, 48, 64, 127)", abl);
+      }
+    }
     if (occ_env == 80) return launch_f16_t<16, 13, 80>(a, hpc, st);
     if (occ_env == 128) return launch_f16_t<16, 13, 128>(a, hpc, st);
     return launch_f16_t<16, 13, 72>(a, hpc, st);

@@ -155,7 +155,8 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // [key]{hi[DH] | lo[DH] | pad} fp16 and read with ldmatrix.trans (xs = this lane's row address for key block 0,
 // dims 0..15, hi).  Two key blocks are in flight on separate accumulators, so an accumulator is touched once per
 // 2*ND MMAs.
-template <int DH, int NT>
+// ABL: precision ablation (common.cuh): bit 2 drops the P_lo X_hi product, bit 3 the P_hi X_lo product.
+template <int DH, int NT, int ABL = 0>
 __device__ __forceinline__ void pv_product16(const float (&P)[NT][4], uint32_t xs, float (&out)[DH / 8][4]) {
   constexpr int ND = DH / 8, NB = (NT + 1) / 2, RB = F16Layout<DH>::RB;
   float acc[2][ND][4];
@@ -185,16 +186,20 @@ __device__ __forceinline__ void pv_product16(const float (&P)[NT][4], uint32_t x
           ldsm_x4_trans(xl[p][np], xs + j * 16 * RB + np * 32 + DH * 2);
         }
       }
+    if constexpr ((ABL & 4) == 0) {
 #pragma unroll
-    for (int p = 0; p < 2; ++p)
-      if (j0 + p < NB)
+      for (int p = 0; p < 2; ++p)
+        if (j0 + p < NB)
 #pragma unroll
-        for (int n = 0; n < ND; ++n) mma_f16(acc[p][n], al[p], xh[p][n >> 1][(n & 1) * 2], xh[p][n >> 1][(n & 1) * 2 + 1]);
+          for (int n = 0; n < ND; ++n) mma_f16(acc[p][n], al[p], xh[p][n >> 1][(n & 1) * 2], xh[p][n >> 1][(n & 1) * 2 + 1]);
+    }
+    if constexpr ((ABL & 8) == 0) {
 #pragma unroll
-    for (int p = 0; p < 2; ++p)
-      if (j0 + p < NB)
+      for (int p = 0; p < 2; ++p)
+        if (j0 + p < NB)
 #pragma unroll
-        for (int n = 0; n < ND; ++n) mma_f16(acc[p][n], ah[p], xl[p][n >> 1][(n & 1) * 2], xl[p][n >> 1][(n & 1) * 2 + 1]);
+          for (int n = 0; n < ND; ++n) mma_f16(acc[p][n], ah[p], xl[p][n >> 1][(n & 1) * 2], xl[p][n >> 1][(n & 1) * 2 + 1]);
+    }
 #pragma unroll
     for (int p = 0; p < 2; ++p)
       if (j0 + p < NB)

@@ -80,6 +80,19 @@ struct LnEpi {
 };
 int ln_stats_parts(int N);  // number of partials per row the tensor-core GEMM writes for N columns
 
+// ---- precision ablation (tools/ablation.py).  Every contraction runs as three tensor-core products
+// (A_lo B_hi + A_hi B_lo + A_hi B_hi); these switches drop individual products so that their effect on the logits and
+// on the top-K sets can be measured.  Off unless the environment variables are set (read per launch; a skipped MMA is
+// a predicate in the single MMA-issuing thread of the GEMMs and a separate template instantiation of the attention
+// kernel: the default path is unchanged).
+//   EDGL_ABL_GEMM = six digits 0..3 for the dense layers qkvt, ao, ff1, ff2, tr, logits: bit 0 drops A_lo W_hi,
+//                   bit 1 drops A_hi W_lo
+//   EDGL_ABL_ATTN = bit mask: 1 Q_lo K_hi, 2 Q_hi K_lo, 4 P_lo [T|V]_hi, 8 P_hi [T|V]_lo, 16 H_lo W1_hi, 32 H_hi W1_lo,
+//                   64 lam_lo M  (attention_f16_kernel, L <= 104 instantiation only)
+extern int g_edgl_stage;      // pipeline stage of the launch in flight (api.cu mark())
+int ablation_gemm_bits();     // bits of EDGL_ABL_GEMM for g_edgl_stage, 0 when unset / not a dense stage
+int ablation_attn_mask();     // EDGL_ABL_ATTN, 0 when unset
+
 // order-preserving unsigned keys of fp32 values and the 64-bit (key, ~index) words the ranking kernels sort:
 // descending order of the word = (value descending, index ascending), tf.nn.top_k's order (Base.py:181)
 __device__ __forceinline__ uint32_t f2key(float f) {

@@ -88,6 +88,7 @@ struct Params {
   const unsigned int* a_amax;  // bits of max|A| (published by A's producer)
   const float* w_inv;          // 1 / sw
   unsigned int* c_amax;        // optional: publish max|C| for the next layer
+  int abl;                     // precision ablation bits (common.cuh), 0 on the product path
 };
 
 template <int BN>
@@ -193,9 +194,10 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             const uint32_t off = k * 32;         // bytes along K inside the 64 B swizzle row
             const uint64_t dah = umma_desc64(a_hi + off), dal = umma_desc64(a_lo + off);
             const uint64_t dbh = umma_desc64(b_hi + off), dbl = umma_desc64(b_lo + off);
-            umma_f16(d_tmem, dal, dbh, idesc, (kb | k) != 0);
-            umma_f16(d_tmem, dah, dbl, idesc, 1);
-            umma_f16(d_tmem, dah, dbh, idesc, 1);
+            uint32_t accum = (kb | k) != 0;  // p.abl: precision ablation (common.cuh), 0 on the product path
+            if (!(p.abl & 1)) { umma_f16(d_tmem, dal, dbh, idesc, accum); accum = 1; }
+            if (!(p.abl & 2)) { umma_f16(d_tmem, dah, dbl, idesc, accum); accum = 1; }
+            umma_f16(d_tmem, dah, dbh, idesc, accum);
           }
           umma_commit(&empty[s]);          // frees the stage when these MMAs have read it
         }
@@ -369,6 +371,7 @@ int launch_gemm_f16(const GemmArgs& a, cudaStream_t st) {
   static const bool gelu_exact = [] { const char* e = getenv("EDGL_GELU"); return e && e[0] == 'e'; }();
   p.gelu_fit = gelu_exact ? 0 : 1;
   p.a_amax = a.a_amax; p.w_inv = winv; p.c_amax = a.c_amax;
+  p.abl = ablation_gemm_bits();
   static const char epi_mode = [] {
     const char* e = getenv("EDGL_TC_EPI");
     return e ? e[0] : 'a';

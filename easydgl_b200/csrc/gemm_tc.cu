@@ -81,6 +81,7 @@ struct Params {
   LnEpi ln;        // fused LayerNorm pieces of the epilogue (common.cuh); all null = off
   TopkFilter flt;  // top-K candidate filter instead of the store (LN_FILT instantiation only)
   const int* run_if;  // device flag or null: return at once when *run_if == 0
+  int abl;            // precision ablation bits (common.cuh), 0 on the product path
   int epi_direct;  // epilogue stores rows straight from TMEM fragments (no shared-memory transpose)
   int has_blo;  // W_lo = W - tf32(W) is pre-computed in global memory (weights are constant after commit): TMA brings
                 // it in like W and the splitter warps only split the activations
@@ -196,9 +197,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             const uint32_t off = k * UK * 4;  // bytes along K inside the 128 B swizzle row
             const uint64_t dah = umma_desc(a_hi + off), dal = umma_desc(a_lo + off);
             const uint64_t dbh = umma_desc(b_hi + off), dbl = umma_desc(b_lo + off);
-            umma_tf32(d_tmem, dal, dbh, idesc, (kb | k) != 0);
-            umma_tf32(d_tmem, dah, dbl, idesc, 1);
-            umma_tf32(d_tmem, dah, dbh, idesc, 1);
+            uint32_t accum = (kb | k) != 0;  // p.abl: precision ablation (common.cuh), 0 on the product path
+            if (!(p.abl & 1)) { umma_tf32(d_tmem, dal, dbh, idesc, accum); accum = 1; }
+            if (!(p.abl & 2)) { umma_tf32(d_tmem, dah, dbl, idesc, accum); accum = 1; }
+            umma_tf32(d_tmem, dah, dbh, idesc, accum);
           }
           umma_commit(&empty[s]);          // frees the stage when these MMAs have read it
         }
@@ -390,6 +392,7 @@ int launch_gemm_tc(const GemmArgs& a, cudaStream_t st) {
   static const bool gelu_exact = [] { const char* e = getenv("EDGL_GELU"); return e && e[0] == 'e'; }();
   p.gelu_fit = gelu_exact ? 0 : 1;
   p.has_blo = has_blo ? 1 : 0;
+  p.abl = ablation_gemm_bits();
   // Epilogue choice.  "direct" (TMEM fragments -> 32-byte sector stores, no shared-memory transpose) relieves the
   // shared-memory port - the resource these GEMMs are bound by - and measures 3-6 % faster when the epilogue has no
   // residual / periodic-bias rows to fetch (FF1, transform, logits); with them the 8-byte loads make it LSU-bound

@@ -470,6 +470,158 @@ __global__ void __launch_bounds__(256) topk_warp_kernel(const float* __restrict_
   if (pp.dest && pp.signal) p2p_signal_when_grid_done(pp.counter, pp.peer_flags, pp.G, pp.my_rank, pp.epoch);
 }
 
+// ---- short rows, second version (default for the column shards of the multi-GPU path): one warp per row, ~40
+// registers, two passes over the row instead of a register-resident copy.  Pass 1 takes 512 GROUP maxima (16 strided
+// groups per lane); the Keff-th largest of them, resolved to its 16 high bits, is a lower bound T0 of the row's Keff-th
+// largest key (at least Keff elements are >= T0).  Pass 2 appends every key >= T0 - typically ~110 of 2251, all ties
+// at the cut included - to a per-warp list in shared memory; the list is sorted by the 128-slot register network
+// (composed (key, ~index) words: value descending, index ascending) and its first Keff entries are the row's top-K,
+// bit for bit what topk_row returns.  Rows with more than 128 candidates (heavy ties, constant rows) are appended to
+// an overflow list that topk_list_kernel works off with the CTA-per-row code.
+template <bool VEC>  // VEC: 16-byte row pitch and base: the row is read as float4 (a lane owns 4 consecutive columns)
+__global__ void __launch_bounds__(256) topk_warp2_kernel(const float* __restrict__ logits, int ld, long long rows, int N,
+                                                         int K, int col_offset, long long out_stride,
+                                                         int32_t* __restrict__ idx_out, float* __restrict__ val_out,
+                                                         int* __restrict__ ovf_rows, unsigned int* __restrict__ ovf_cnt) {
+  __shared__ unsigned long long s_list[8][128];
+  __shared__ unsigned int s_cnt[8];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + w;
+  if (row >= rows) return;  // warp-uniform; no block-wide barrier below
+  const float* p = logits + row * ld;
+  const int Keff = K < N ? K : N;
+  const int npl = (N + 31) >> 5;
+  const int n4 = (N + 3) >> 2, nit = (n4 + 31) >> 5;  // VEC: float4 words per row, iterations of a warp over them
+  const float4* p4 = reinterpret_cast<const float4*>(p);
+  uint32_t gm[16];
+#pragma unroll
+  for (int g = 0; g < 16; ++g) gm[g] = 0u;
+  if constexpr (VEC) {
+    for (int j0 = 0; j0 < nit; j0 += 16) {
+#pragma unroll
+      for (int g = 0; g < 16; ++g) {
+        const int q = (j0 + g) * 32 + lane;
+        if (q < n4) {
+          const float4 x = p4[q];
+          const int i = 4 * q;  // columns i .. i+3; those >= N (row padding) count as key 0, below every float
+          const uint32_t k0 = f2key(x.x), k1 = i + 1 < N ? f2key(x.y) : 0u, k2 = i + 2 < N ? f2key(x.z) : 0u,
+                         k3 = i + 3 < N ? f2key(x.w) : 0u;
+          gm[g] = max(max(gm[g], k0), max(k1, max(k2, k3)));
+        }
+      }
+    }
+  } else {
+    for (int j0 = 0; j0 < npl; j0 += 16) {
+#pragma unroll
+      for (int g = 0; g < 16; ++g) {
+        const int i = (j0 + g) * 32 + lane;
+        const uint32_t key = i < N ? f2key(p[i]) : 0u;  // 0 is below the key of every float
+        gm[g] = max(gm[g], key);
+      }
+    }
+  }
+  uint32_t T0 = 0;
+#pragma unroll 1
+  for (int bit = 31; bit >= 16; --bit) {
+    const uint32_t c = T0 | (1u << bit);
+    int cnt = 0;
+#pragma unroll
+    for (int g = 0; g < 16; ++g) cnt += (gm[g] >= c) ? 1 : 0;
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if (cnt >= Keff) T0 = c;
+  }
+  if (lane == 0) s_cnt[w] = 0u;
+  __syncwarp();
+  auto take = [&](uint32_t key, int i) {
+    if (i < N && key >= T0) {
+      const unsigned int pos = atomicAdd(&s_cnt[w], 1u);
+      if (pos < 128u) s_list[w][pos] = compose(key, (uint32_t)i);
+    }
+  };
+  if constexpr (VEC) {
+#pragma unroll 4
+    for (int j = 0; j < nit; ++j) {
+      const int q = j * 32 + lane;
+      if (q < n4) {
+        const float4 x = p4[q];
+        take(f2key(x.x), 4 * q);
+        take(f2key(x.y), 4 * q + 1);
+        take(f2key(x.z), 4 * q + 2);
+        take(f2key(x.w), 4 * q + 3);
+      }
+    }
+  } else {
+#pragma unroll 8
+    for (int j = 0; j < npl; ++j) {
+      const int i = j * 32 + lane;
+      if (i < N) take(f2key(p[i]), i);
+    }
+  }
+  __syncwarp();
+  const unsigned int total = s_cnt[w];
+  if (total > 128u) {  // warp-uniform
+    if (lane == 0) ovf_rows[atomicAdd(ovf_cnt, 1u)] = (int)row;
+    return;
+  }
+  unsigned long long v[4];  // sort slot e lives in v[e / 32] of lane e % 32
+#pragma unroll
+  for (int m = 0; m < 4; ++m) v[m] = (unsigned int)(m * 32 + lane) < total ? s_list[w][m * 32 + lane] : 0ull;
+#pragma unroll
+  for (int kk = 2; kk <= 128; kk <<= 1) {
+#pragma unroll
+    for (int j = kk >> 1; j > 0; j >>= 1) {
+      if (j >= 32) {
+        const int dm = j >> 5;
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          if ((m & dm) == 0) {
+            const int e = m * 32 + lane;
+            const bool desc = (e & kk) == 0;
+            const unsigned long long a = v[m], b = v[m | dm];
+            const bool sw = desc ? (a < b) : (a > b);
+            v[m] = sw ? b : a;
+            v[m | dm] = sw ? a : b;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int m = 0; m < 4; ++m) v[m] = cmpx64(v[m], m * 32 + lane, kk, j);
+      }
+    }
+  }
+  int32_t* io = idx_out + row * out_stride;
+  float* vo = val_out + row * out_stride;
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    const int e = m * 32 + lane;
+    if (e < K) {
+      if (e < Keff) {
+        io[e] = (int32_t)(0xffffffffu - (uint32_t)(v[m] & 0xffffffffull)) + col_offset;
+        vo[e] = key2f((uint32_t)(v[m] >> 32));
+      } else {
+        io[e] = -1;
+        vo[e] = -INFINITY;
+      }
+    }
+  }
+}
+
+// the rows topk_warp2_kernel could not finish: CTA-per-row code over the overflow list (a fixed, small grid)
+__global__ void __launch_bounds__(256) topk_list_kernel(const float* __restrict__ logits, int ld, int N, int K, int KP,
+                                                        int col_offset, long long out_stride,
+                                                        int32_t* __restrict__ idx_out, float* __restrict__ val_out,
+                                                        const int* __restrict__ ovf_rows,
+                                                        const unsigned int* __restrict__ ovf_cnt) {
+  extern __shared__ __align__(16) unsigned long long cand[];  // max(KP, kCandCap) entries
+  const unsigned int n = *ovf_cnt;
+  const int vec = (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(logits) & 15) == 0);
+  for (unsigned int r = blockIdx.x; r < n; r += gridDim.x) {
+    const long long row = ovf_rows[r];
+    topk_row(logits + row * ld, vec, N, K, KP, col_offset, cand, idx_out + row * out_stride, val_out + row * out_stride);
+    __syncthreads();
+  }
+}
+
 static int next_pow2(int v) {
   int p = 1;
   while (p < v) p <<= 1;
@@ -491,6 +643,32 @@ int launch_topk(const float* logits, int ld, int B, int N, int K, int col_offset
   // instructions per row.
   const char* we = getenv("EDGL_TOPK_WARP");
   const bool use_warp = we != nullptr && we[0] == '1';
+  // second warp-per-row version: the default for short rows (EDGL_TOPK_WARP=0 keeps the CTA kernel, =1 the first version)
+  static const int warp_max_n = [] { const char* e = getenv("EDGL_TOPK_WARP_MAXN"); return e ? atoi(e) : 4096; }();
+  if (!(we && (we[0] == '0' || we[0] == '1')) && !p2p && !run_if && K <= 128 && N >= 256 && N <= warp_max_n && B >= 64) {
+    static int* ovf = nullptr;       // [cap] row ids + one counter in front
+    static long long ovf_cap = 0;
+    if (B > ovf_cap) {
+      if (ovf) cudaFree(ovf);
+      EDGL_CUDA(cudaMalloc(&ovf, ((size_t)B + 4) * sizeof(int)));
+      ovf_cap = B;
+    }
+    unsigned int* cnt = reinterpret_cast<unsigned int*>(ovf);
+    EDGL_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned int), st));
+    const bool vec = (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(logits) & 15) == 0) && ld >= ((N + 3) & ~3);
+    if (vec)
+      topk_warp2_kernel<true><<<(unsigned)((B + 7) / 8), 256, 0, st>>>(logits, ld, B, N, K, col_offset, out_stride, idx,
+                                                                       val, ovf + 4, cnt);
+    else
+      topk_warp2_kernel<false><<<(unsigned)((B + 7) / 8), 256, 0, st>>>(logits, ld, B, N, K, col_offset, out_stride, idx,
+                                                                        val, ovf + 4, cnt);
+    EDGL_LAUNCH_CHECK();
+    const int KP2 = next_pow2(K);
+    const size_t smem2 = (size_t)(KP2 > kCandCap ? KP2 : kCandCap) * 8;
+    topk_list_kernel<<<296, 256, smem2, st>>>(logits, ld, N, K, KP2, col_offset, out_stride, idx, val, ovf + 4, cnt);
+    EDGL_LAUNCH_CHECK();
+    return 0;
+  }
   if (use_warp && !run_if && K <= 128 && N <= 32 * 96 && B >= 64) {
     const unsigned grid = (unsigned)((B + 7) / 8);
     if (N <= 32 * 32) topk_warp_kernel<32><<<grid, 256, 0, st>>>(logits, ld, B, N, K, col_offset, out_stride, idx, val, pp);

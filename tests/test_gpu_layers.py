@@ -245,13 +245,17 @@ def test_topk_ties_and_masking():
 
 
 @pytest.mark.parametrize("N,K", [(31, 100), (1000, 100), (2251, 100), (3072, 100), (2251, 7), (1500, 128)])
-@pytest.mark.parametrize("warp", ["1", "0"])
+@pytest.mark.parametrize("warp", ["default", "1", "0"])
 def test_topk_short_rows_warp_kernel(N, K, warp, monkeypatch):
-    """Many short rows (the column shards of the multi-GPU path) through the one-warp-per-row kernel (EDGL_TOPK_WARP=1,
-    opt-in) and the default CTA-per-row kernel: bit-identical to tf.nn.top_k semantics, including ties at the cut,
-    -inf and rows shorter than K."""
+    """Many short rows (the column shards of the multi-GPU path) through the two-pass one-warp-per-row kernel with its
+    overflow list (the default for 256 <= N <= 4096), the register-resident first version (EDGL_TOPK_WARP=1) and the
+    CTA-per-row kernel (EDGL_TOPK_WARP=0): bit-identical to tf.nn.top_k semantics, including ties at the cut, -inf and
+    rows shorter than K."""
     from easydgl_b200 import engine
-    monkeypatch.setenv("EDGL_TOPK_WARP", warp)
+    if warp == "default":
+        monkeypatch.delenv("EDGL_TOPK_WARP", raising=False)
+    else:
+        monkeypatch.setenv("EDGL_TOPK_WARP", warp)
     g = torch.Generator().manual_seed(60 + N + K)
     B = 300
     logits = torch.randn(B, N, generator=g)

@@ -644,7 +644,9 @@ int launch_topk(const float* logits, int ld, int B, int N, int K, int col_offset
   const char* we = getenv("EDGL_TOPK_WARP");
   const bool use_warp = we != nullptr && we[0] == '1';
   // second warp-per-row version: the default for short rows (EDGL_TOPK_WARP=0 keeps the CTA kernel, =1 the first version)
-  static const int warp_max_n = [] { const char* e = getenv("EDGL_TOPK_WARP_MAXN"); return e ? atoi(e) : 4096; }();
+  // measured against the CTA kernel (tools/bench_topk_rows.py): 32768 x 2252: 0.176 vs 0.387 ms; 16384 x 6252: 0.200 vs
+  // 0.256; 8192 x 12504: 0.186 vs 0.173; 4096 x 18004: 0.201 vs 0.114 - so rows of up to 8192 columns take it
+  static const int warp_max_n = [] { const char* e = getenv("EDGL_TOPK_WARP_MAXN"); return e ? atoi(e) : 8192; }();
   if (!(we && (we[0] == '0' || we[0] == '1')) && !p2p && !run_if && K <= 128 && N >= 256 && N <= warp_max_n && B >= 64) {
     static int* ovf = nullptr;       // [cap] row ids + one counter in front
     static long long ovf_cap = 0;

@@ -360,3 +360,71 @@ def test_tg_attention_decomposition_matches_literal():
         out[:, :, sl] = P @ A_v[:, :, sl] + TC @ w["v_w"][C:, sl]
     got = O.layernorm_last(out @ w["o_w"] + w["o_b"] + q2, w["ln_g"], w["ln_b"])
     assert float((got - ref).abs().max()) < 1e-10
+
+
+def _ti_tf_inputs(N=2, T=7, C=8, seed=3):
+    g = torch.Generator().manual_seed(seed)
+    q = torch.randn(N, T, C, generator=g, dtype=torch.float64)
+    k = torch.randn(N, T, C, generator=g, dtype=torch.float64)
+    k[0, :2] = 0.0   # two padded keys in sequence 0
+    w = {n: torch.randn(C, C, generator=g, dtype=torch.float64) for n in ("q_w", "k_w", "v_w")}
+    w.update({n: torch.randn(C, generator=g, dtype=torch.float64) for n in ("q_b", "k_b", "v_b")})
+    return g, q, k, w
+
+
+def test_ti_attention_restatement_invariants():
+    """TiMultiHeadAttention (temporal.py:37-109): with zero position / interval tables it is plain masked multi-head
+    attention + residual; padded keys get no weight; causality blinds the future; an all-zero query row gets its
+    attention output zeroed (query masking, temporal.py:87-90) and keeps only the residual."""
+    g, q, k, w = _ti_tf_inputs()
+    N, T, C = q.shape
+    h = 2
+    iv = torch.randint(0, 5, (N, T, T), generator=g)
+    z_pos, z_tab = torch.zeros(T, C, dtype=torch.float64), torch.zeros(5, C, dtype=torch.float64)
+    out = O.ti_attention(q, k, iv, w, z_pos, z_pos, z_tab, z_tab, h, causality=True)
+    # plain attention by hand
+    Q, K, V = q @ w["q_w"] + w["q_b"], k @ w["k_w"] + w["k_b"], k @ w["v_w"] + w["v_b"]
+    ref = torch.zeros_like(out)
+    dh = C // h
+    for hd in range(h):
+        sl = slice(hd * dh, (hd + 1) * dh)
+        s = Q[:, :, sl] @ K[:, :, sl].transpose(1, 2) / dh ** 0.5
+        km = (k.abs().sum(-1) != 0).unsqueeze(1).expand(N, T, T)
+        s = torch.where(km, s, torch.full_like(s, O.MASK_FILL))
+        s = torch.where(torch.tril(torch.ones(T, T)) == 0, torch.full_like(s, O.MASK_FILL), s)
+        ref[:, :, sl] = torch.softmax(s, -1) @ V[:, :, sl]
+    assert float((out - (ref + q)).abs().max()) < 1e-12
+    # a non-trivial interval table changes the result, and only through intervals actually used
+    tab = torch.randn(5, C, generator=g, dtype=torch.float64)
+    out2 = O.ti_attention(q, k, iv, w, z_pos, z_pos, tab, tab, h, causality=True)
+    assert float((out2 - out).abs().max()) > 1e-3
+    # query masking: zero query row -> output row = residual = 0
+    q2 = q.clone()
+    q2[1, 3] = 0.0
+    out3 = O.ti_attention(q2, k, iv, w, z_pos, z_pos, tab, tab, h, causality=True)
+    assert float(out3[1, 3].abs().max()) == 0.0
+
+
+def test_tf_attention_restatement_invariants():
+    """TfMultiHeadAttention (temporal.py:126-185): the Bochner / Mercer code cos(dt w + phi) enters the scores only;
+    with w = 0, phi = pi/2 the code vanishes (cos = 0 up to rounding) and the layer is plain attention."""
+    g, q, k, w = _ti_tf_inputs(seed=8)
+    N, T, C = q.shape
+    iv = torch.rand(N, T, T, generator=g) * 10.0
+    z_pos = torch.zeros(T, C, dtype=torch.float64)
+    zero_code = O.tf_attention(q, k, iv, w, z_pos, torch.zeros(C), torch.full((C,), float(np.pi / 2)), 2, True)
+    ti_plain = O.ti_attention(q, k, torch.zeros(N, T, T, dtype=torch.int64), w, z_pos, z_pos,
+                              torch.zeros(1, C, dtype=torch.float64), torch.zeros(1, C, dtype=torch.float64), 2, True)
+    # Tf has no query masking; these inputs have no all-zero query rows, so the two must agree
+    assert float((zero_code - ti_plain).abs().max()) < 1e-6
+    with_code = O.tf_attention(q, k, iv, w, z_pos, torch.linspace(0, 9, C), torch.zeros(C), 2, True)
+    assert float((with_code - zero_code).abs().max()) > 1e-3
+    # causality: rows 0..2 of the unpadded sequence see keys 0..2 only.  (Sequence 0 has its first two keys padded: its
+    # rows 0, 1 have every visible key masked, all scores equal the fill value and the softmax is uniform over ALL keys,
+    # future ones included - the reference's behaviour, Q8.)
+    k2 = k.clone()
+    k2[:, 3:] += 1.0
+    a = O.tf_attention(q, k, iv, w, z_pos, torch.linspace(0, 9, C), torch.zeros(C), 2, True)
+    b = O.tf_attention(q, k2, iv, w, z_pos, torch.linspace(0, 9, C), torch.zeros(C), 2, True)
+    assert float((a[1, :3] - b[1, :3]).abs().max()) < 1e-12
+    assert float((a[0, :2] - b[0, :2]).abs().max()) > 1e-3

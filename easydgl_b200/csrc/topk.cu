@@ -8,6 +8,10 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include "common.cuh"
 
 namespace edgl {
@@ -648,12 +652,25 @@ int launch_topk(const float* logits, int ld, int B, int N, int K, int col_offset
   // 0.256; 8192 x 12504: 0.186 vs 0.173; 4096 x 18004: 0.201 vs 0.114 - so rows of up to 8192 columns take it
   static const int warp_max_n = [] { const char* e = getenv("EDGL_TOPK_WARP_MAXN"); return e ? atoi(e) : 8192; }();
   if (!(we && (we[0] == '0' || we[0] == '1')) && !p2p && !run_if && K <= 128 && N >= 256 && N <= warp_max_n && B >= 64) {
-    static int* ovf = nullptr;       // [cap] row ids + one counter in front
-    static long long ovf_cap = 0;
-    if (B > ovf_cap) {
-      if (ovf) cudaFree(ovf);
-      EDGL_CUDA(cudaMalloc(&ovf, ((size_t)B + 4) * sizeof(int)));
-      ovf_cap = B;
+    // overflow list: one buffer per (device, stream) - launches on different streams must not share it - grown on
+    // demand and kept (a handful of entries: one process drives one GPU with one or two streams)
+    struct OvfBuf { int* p = nullptr; long long cap = 0; };
+    static std::mutex ovf_mu;
+    static std::map<std::pair<int, cudaStream_t>, OvfBuf> ovf_map;
+    int* ovf = nullptr;  // [4 ints: counter + padding][cap row ids]
+    {
+      int dev = 0;
+      EDGL_CUDA(cudaGetDevice(&dev));
+      std::lock_guard<std::mutex> lock(ovf_mu);
+      OvfBuf& ob = ovf_map[std::make_pair(dev, st)];
+      if (B > ob.cap) {
+        if (ob.p) EDGL_CUDA(cudaFree(ob.p));  // synchronises: the old list is no longer in use
+        ob.p = nullptr;
+        ob.cap = 0;
+        EDGL_CUDA(cudaMalloc(&ob.p, ((size_t)B + 4) * sizeof(int)));
+        ob.cap = B;
+      }
+      ovf = ob.p;
     }
     unsigned int* cnt = reinterpret_cast<unsigned int*>(ovf);
     EDGL_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned int), st));
@@ -760,11 +777,7 @@ int launch_topk_select(const unsigned long long* cand, const unsigned int* cnt, 
   int hs = 256;
   while (hs < 2 * seen_len) hs <<= 1;
   const size_t smem = (size_t)cap * 8 + (size_t)hs * 4;
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
-    EDGL_CUDA(cudaFuncSetAttribute(topk_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = smem;
-  }
+  EDGL_CUDA(cudaFuncSetAttribute(topk_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   topk_select_kernel<<<B, 256, smem, st>>>(cand, cnt, cap, K, col_offset, seen, seen_len, seen_stride, col0, col1,
                                            out_stride, idx, val, redo, hs);
   EDGL_LAUNCH_CHECK();
